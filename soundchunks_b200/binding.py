@@ -1,0 +1,419 @@
+"""ctypes binding of libgsc_cuda.so (include/gsc_cuda.h).
+
+This is the Python face of the C ABI; there is NO CPU fallback here or in the
+library: if the shared object is missing, or no sm_100 device is usable, every
+call raises.  numpy arrays in, numpy arrays out.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libgsc_cuda.so")
+
+#: every symbol include/gsc_cuda.h declares (checked by the CPU test-suite)
+EXPORTS = [
+    "yakmo_create", "yakmo_destroy", "yakmo_load_train_data", "yakmo_train_on_data", "yakmo_get_centroids",
+    "ann_kdtree_create", "ann_kdtree_destroy", "ann_kdtree_search", "ann_kdtree_pri_search",
+    "ann_kdtree_search_multi", "ann_kdtree_pri_search_multi",
+    "gsc_last_error", "gsc_device_count", "gsc_create", "gsc_destroy", "gsc_ctx_device", "gsc_ctx_stream",
+    "gsc_synchronize", "gsc_get_stats", "gsc_reset_stats",
+    "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
+    "gsc_assign", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
+    "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
+    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact",
+]
+
+
+class GscError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("chunk_size", C.c_int32), ("chunk_bit_depth", C.c_int32), ("chunks_per_frame", C.c_int32),
+                ("precision", C.c_int32), ("max_passes", C.c_int32), ("kmeans_mode", C.c_int32),
+                ("lloyd_iters", C.c_int32), ("reserved", C.c_int32)]
+
+
+class FrameDesc(C.Structure):
+    _fields_ = [("pcm", C.c_void_p), ("stride", C.c_int64), ("channels", C.c_int32), ("samples", C.c_int32)]
+
+
+class FrameResultC(C.Structure):
+    _fields_ = [("dict", C.c_void_p), ("datten", C.c_void_p), ("index", C.c_void_p), ("attr", C.c_void_p),
+                ("N", C.c_int32), ("R", C.c_int32), ("divider", C.c_int32), ("passes", C.c_int32),
+                ("err", C.c_double), ("overfull", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("last_stage_ms", C.c_double * 8)]
+
+
+STAGE_NAMES = ["divider", "chunks", "seed", "kmeans", "dictionary", "knnfit", "finalize", "total"]
+
+
+@dataclass
+class FrameResult:
+    N: int
+    R: int
+    divider: int
+    passes: int
+    err: float
+    dict: np.ndarray      # int16 [R][cs]
+    datten: np.ndarray    # uint8 [R]
+    index: np.ndarray     # int32 [N]
+    attr: np.ndarray      # uint8 [N]  bit1 Negative, bit0 Reversed
+    overfull: int
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libgsc_cuda.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise GscError(f"{SO_PATH} is missing: build it with `python -m soundchunks_b200.build` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(SO_PATH)
+    L.gsc_last_error.restype = C.c_char_p
+    L.gsc_create.restype = C.c_void_p
+    L.gsc_create.argtypes = [C.c_int]
+    L.gsc_destroy.argtypes = [C.c_void_p]
+    L.gsc_ctx_stream.restype = C.c_void_p
+    L.gsc_ctx_stream.argtypes = [C.c_void_p]
+    L.gsc_ctx_device.argtypes = [C.c_void_p]
+    L.gsc_synchronize.argtypes = [C.c_void_p]
+    L.gsc_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.gsc_reset_stats.argtypes = [C.c_void_p]
+    L.yakmo_create.restype = C.c_void_p
+    L.yakmo_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.yakmo_destroy.argtypes = [C.c_void_p]
+    L.yakmo_load_train_data.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.yakmo_train_on_data.argtypes = [C.c_void_p, C.c_void_p]
+    L.yakmo_get_centroids.argtypes = [C.c_void_p, C.c_void_p]
+    L.ann_kdtree_create.restype = C.c_void_p
+    L.ann_kdtree_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.ann_kdtree_destroy.argtypes = [C.c_void_p]
+    for n in ("ann_kdtree_search", "ann_kdtree_pri_search"):
+        getattr(L, n).restype = C.c_int32
+        getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    for n in ("ann_kdtree_search_multi", "ann_kdtree_pri_search_multi"):
+        getattr(L, n).restype = None
+        getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float]
+    _lib = L
+    return L
+
+
+def _vp(a: Optional[np.ndarray]):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _pcm(pcm) -> np.ndarray:
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    if pcm.ndim == 1:
+        pcm = pcm[None, :]
+    return pcm
+
+
+def device_count() -> int:
+    return int(load_library().gsc_device_count())
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    load_library().gsc_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    """One device + stream + scratch (gsc_ctx)."""
+
+    def __init__(self, device: int = -1):
+        self.L = load_library()
+        self.h = self.L.gsc_create(device)
+        if not self.h:
+            raise GscError(self.L.gsc_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gsc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise GscError(f"libgsc_cuda error {rc}: {self.L.gsc_last_error().decode()}")
+
+    @property
+    def device(self) -> int:
+        return int(self.L.gsc_ctx_device(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.gsc_ctx_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._ck(self.L.gsc_synchronize(self.h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self.L.gsc_get_stats(self.h, C.byref(s)))
+        return dict(kernel_launches=int(s.kernel_launches), h2d_bytes=int(s.h2d_bytes),
+                    d2h_bytes=int(s.d2h_bytes),
+                    stage_ms={n: float(s.last_stage_ms[i]) for i, n in enumerate(STAGE_NAMES)})
+
+    def reset_stats(self):
+        self._ck(self.L.gsc_reset_stats(self.h))
+
+    def fp32_peak_tflops(self) -> float:
+        v = C.c_double(0)
+        self._ck(self.L.gsc_fp32_peak_probe(C.c_void_p(self.h), C.byref(v)))
+        return v.value
+
+    # ---- per-frame stages -------------------------------------------------
+    def find_attenuation_divider(self, pcm, cs=4, bits=12, return_v=False):
+        pcm = _pcm(pcm)
+        Cn, S = pcm.shape
+        d = C.c_int(0)
+        v = np.zeros(64, np.float64)
+        self._ck(self.L.gsc_find_attenuation_divider(C.c_void_p(self.h), _vp(pcm), C.c_int64(S), Cn, S, cs, bits,
+                                                     C.byref(d), _vp(v)))
+        return (d.value, v) if return_v else d.value
+
+    def make_chunks(self, pcm, cs=4, bits=12, divider=6):
+        """-> attr u8[N], atten u8[N], feat f32[N][2cs], dst i16[N][cs]"""
+        pcm = _pcm(pcm)
+        Cn, S = pcm.shape
+        N = ((S - 1) // cs + 1) * Cn
+        attr = np.zeros(N, np.uint8)
+        atten = np.zeros(N, np.uint8)
+        feat = np.zeros((N, 2 * cs), np.float32)
+        dst = np.zeros((N, cs), np.int16)
+        self._ck(self.L.gsc_make_chunks(C.c_void_p(self.h), _vp(pcm), C.c_int64(S), Cn, S, cs, bits, divider,
+                                        _vp(attr), _vp(atten), _vp(feat), _vp(dst)))
+        return attr, atten, feat, dst
+
+    def yakmo(self, X, K, init_type=1, max_iter=0):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        N, D = X.shape
+        cen = np.zeros((K, D), np.float32)
+        labels = np.zeros(N, np.int32)
+        seeds = np.zeros(K, np.int32)
+        self._ck(self.L.gsc_yakmo(C.c_void_p(self.h), _vp(X), N, D, K, init_type, max_iter, _vp(cen), _vp(labels),
+                                  _vp(seeds)))
+        return cen, labels, seeds
+
+    def knn_scan_reduce(self, X, centroids, precision=3, max_passes=100):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        cen = np.array(centroids, dtype=np.float32, order="C", copy=True)
+        N, D = X.shape
+        labels = np.zeros(N, np.int32)
+        passes = C.c_int(0)
+        err = C.c_double(0)
+        self._ck(self.L.gsc_knn_scan_reduce(C.c_void_p(self.h), _vp(X), N, D, _vp(cen), cen.shape[0], precision,
+                                            max_passes, _vp(labels), C.byref(passes), C.byref(err)))
+        return cen, labels, passes.value, err.value
+
+    def lloyd(self, X, centroids, iters):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        cen = np.array(centroids, dtype=np.float32, order="C", copy=True)
+        N, D = X.shape
+        labels = np.zeros(N, np.int32)
+        self._ck(self.L.gsc_lloyd(C.c_void_p(self.h), _vp(X), N, D, _vp(cen), cen.shape[0], iters, _vp(labels)))
+        return cen, labels
+
+    def assign(self, X, centroids):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        cen = np.ascontiguousarray(centroids, dtype=np.float32)
+        N, D = X.shape
+        labels = np.zeros(N, np.int32)
+        dist = np.zeros(N, np.float32)
+        self._ck(self.L.gsc_assign(C.c_void_p(self.h), _vp(X), N, D, _vp(cen), cen.shape[0], _vp(labels), _vp(dist)))
+        return labels, dist
+
+    def build_dictionary(self, labels, pcm, attr, K, cs=4, bits=12, divider=6):
+        pcm = _pcm(pcm)
+        Cn, S = pcm.shape
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        attr = np.ascontiguousarray(attr, dtype=np.uint8)
+        N = len(labels)
+        out = dict(means=np.zeros((K, cs), np.float32), order=np.zeros(K, np.int32), counts=np.zeros(K, np.int32),
+                   dict=np.zeros((K, cs), np.int16), datten=np.zeros(K, np.uint8), dattr=np.zeros(K, np.uint8),
+                   entry=np.zeros(N, np.int32))
+        self._ck(self.L.gsc_build_dictionary(C.c_void_p(self.h), _vp(labels), _vp(pcm), C.c_int64(S), Cn, S, _vp(attr),
+                                             cs, K, bits, divider, _vp(out["means"]), _vp(out["order"]),
+                                             _vp(out["counts"]), _vp(out["dict"]), _vp(out["datten"]),
+                                             _vp(out["dattr"]), _vp(out["entry"])))
+        return out
+
+    def knnfit(self, dic, datten, pcm, cs=4, bits=12, divider=6):
+        pcm = _pcm(pcm)
+        Cn, S = pcm.shape
+        dic = np.ascontiguousarray(dic, dtype=np.int16)
+        datten = np.ascontiguousarray(datten, dtype=np.uint8)
+        R = dic.shape[0]
+        N = ((S - 1) // cs + 1) * Cn
+        out = dict(best=np.zeros(N, np.int32), use=np.zeros(R, np.int32), band=np.zeros(N, np.int32))
+        self._ck(self.L.gsc_knnfit(C.c_void_p(self.h), _vp(dic), _vp(datten), R, cs, bits, divider, _vp(pcm),
+                                   C.c_int64(S), Cn, S, _vp(out["best"]), _vp(out["use"]), _vp(out["band"])))
+        return out
+
+    def finalize_dictionary(self, use):
+        use = np.ascontiguousarray(use, dtype=np.int32)
+        R = len(use)
+        remap = np.zeros(R, np.int32)
+        order = np.zeros(R, np.int32)
+        n = C.c_int(0)
+        self._ck(self.L.gsc_finalize_dictionary(C.c_void_p(self.h), _vp(use), R, _vp(remap), _vp(order), C.byref(n)))
+        return n.value, remap, order[:n.value]
+
+    # ---- whole frames -------------------------------------------------------
+    def encode_frames(self, frames: Sequence[np.ndarray], params: Optional[Params] = None, **kw) -> List[FrameResult]:
+        """frames: list of planar int16 [C][S] arrays (host). One gsc_encode_frames call."""
+        p = params if params is not None else default_params(**kw)
+        fr = [_pcm(f) for f in frames]
+        n = len(fr)
+        desc = (FrameDesc * n)()
+        res = (FrameResultC * n)()
+        cap = int(self.L.gsc_dict_capacity(C.byref(p), 0, 0))
+        cs = p.chunk_size
+        bufs = []
+        for i, f in enumerate(fr):
+            Cn, S = f.shape
+            N = ((S - 1) // cs + 1) * Cn
+            desc[i] = FrameDesc(f.ctypes.data, S, Cn, S)
+            d = np.zeros((max(cap, 1), cs), np.int16)
+            a = np.zeros(max(cap, 1), np.uint8)
+            ix = np.zeros(N, np.int32)
+            at = np.zeros(N, np.uint8)
+            bufs.append((d, a, ix, at))
+            res[i].dict, res[i].datten, res[i].index, res[i].attr = d.ctypes.data, a.ctypes.data, ix.ctypes.data, at.ctypes.data
+        self._ck(self.L.gsc_encode_frames(C.c_void_p(self.h), desc, n, C.byref(p), res))
+        out = []
+        for i in range(n):
+            d, a, ix, at = bufs[i]
+            R = res[i].R
+            out.append(FrameResult(N=res[i].N, R=R, divider=res[i].divider, passes=res[i].passes, err=res[i].err,
+                                   dict=d[:R].copy(), datten=a[:R].copy(), index=ix, attr=at,
+                                   overfull=res[i].overfull))
+        return out
+
+    def encode_frames_dev(self, dev_ptr: int, layout: Sequence[tuple], params: Params):
+        """Device-resident PCM: layout = [(offset_samples, stride, channels, samples), ...] into the
+        int16 buffer at dev_ptr.  Results stay on the device (fetch_results)."""
+        n = len(layout)
+        desc = (FrameDesc * n)()
+        for i, (off, stride, Cn, S) in enumerate(layout):
+            desc[i] = FrameDesc(dev_ptr + 2 * off, stride, Cn, S)
+        self._ck(self.L.gsc_encode_frames_dev(C.c_void_p(self.h), desc, n, C.byref(params)))
+
+    def fetch_results(self, layout: Sequence[tuple], params: Params) -> List[FrameResult]:
+        n = len(layout)
+        res = (FrameResultC * n)()
+        cap = int(self.L.gsc_dict_capacity(C.byref(params), 0, 0))
+        cs = params.chunk_size
+        bufs = []
+        for i, (off, stride, Cn, S) in enumerate(layout):
+            N = ((S - 1) // cs + 1) * Cn
+            d = np.zeros((max(cap, 1), cs), np.int16)
+            a = np.zeros(max(cap, 1), np.uint8)
+            ix = np.zeros(N, np.int32)
+            at = np.zeros(N, np.uint8)
+            bufs.append((d, a, ix, at))
+            res[i].dict, res[i].datten, res[i].index, res[i].attr = d.ctypes.data, a.ctypes.data, ix.ctypes.data, at.ctypes.data
+        self._ck(self.L.gsc_fetch_results(C.c_void_p(self.h), n, res))
+        out = []
+        for i in range(n):
+            d, a, ix, at = bufs[i]
+            R = res[i].R
+            out.append(FrameResult(N=res[i].N, R=R, divider=res[i].divider, passes=res[i].passes, err=res[i].err,
+                                   dict=d[:R].copy(), datten=a[:R].copy(), index=ix, attr=at,
+                                   overfull=res[i].overfull))
+        return out
+
+
+# ---- legacy ABI helpers (what extern.pas binds) ------------------------------
+def _row_ptrs(a: np.ndarray):
+    rows = (C.c_void_p * a.shape[0])()
+    base = a.ctypes.data
+    stride = a.strides[0]
+    for i in range(a.shape[0]):
+        rows[i] = base + i * stride
+    return rows
+
+
+def legacy_yakmo(X: np.ndarray, k: int, max_iter: int = 0, init_type: int = 1):
+    """yakmo_create .. yakmo_destroy exactly as enc:824-828 drives them."""
+    L = load_library()
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    N, D = X.shape
+    h = L.yakmo_create(k, 1, max_iter, init_type, 0, 0, 0)
+    if not h:
+        raise GscError(L.gsc_last_error().decode())
+    try:
+        L.yakmo_load_train_data(h, N, D, _row_ptrs(X))
+        labels = np.zeros(N, np.int32)
+        L.yakmo_train_on_data(h, _vp(labels))
+        cen = np.zeros((k, D), np.float32)
+        L.yakmo_get_centroids(h, _row_ptrs(cen))
+    finally:
+        L.yakmo_destroy(h)
+    return cen, labels
+
+
+class LegacyAnn:
+    """ann_kdtree_* as ext:118-123 binds them."""
+
+    def __init__(self, pts: np.ndarray):
+        self.L = load_library()
+        self.pts = np.ascontiguousarray(pts, dtype=np.float32)
+        n, dd = self.pts.shape
+        self.h = self.L.ann_kdtree_create(_row_ptrs(self.pts), n, dd, 1, 0)
+        if not self.h:
+            raise GscError(self.L.gsc_last_error().decode())
+
+    def search(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        err = C.c_float(0)
+        idx = self.L.ann_kdtree_search(self.h, _vp(q), 0.0, C.byref(err))
+        return int(idx), float(err.value)
+
+    def pri_search_multi(self, q, cnt):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        idxs = np.zeros(cnt, np.int32)
+        errs = np.zeros(cnt, np.float32)
+        self.L.ann_kdtree_pri_search_multi(self.h, _vp(idxs), _vp(errs), cnt, _vp(q), 0.0)
+        return idxs, errs
+
+    def close(self):
+        if self.h:
+            self.L.ann_kdtree_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,1046 @@
+// gsc_api.cu -- libgsc_cuda.so: context, frame pipeline, C ABI (include/gsc_cuda.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -shared
+//
+// No CPU fallback: every entry point fails loudly when no sm_100 device works.
+#include "../../include/gsc_cuda.h"
+
+#include <cuda_runtime.h>
+#include <xmmintrin.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "gsc_kernels.cuh"
+#include "gsc_online.cuh"
+
+// ---------------------------------------------------------------------------
+// error handling, FP environment
+// ---------------------------------------------------------------------------
+static thread_local std::string t_err;
+
+static int set_err(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+
+// The FreePascal host runs with FP exceptions unmasked: mask
+// them for the duration of every entry point, restore on exit.
+struct FpGuard {
+    unsigned old;
+    FpGuard() { old = _mm_getcsr(); _mm_setcsr((old | 0x1f80u) & ~0x3fu); }
+    ~FpGuard() { _mm_setcsr(old); }
+};
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return set_err(GSC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                           __FILE__, __LINE__);                                               \
+    } while (0)
+
+extern "C" const char *gsc_last_error(void) { return t_err.c_str(); }
+
+extern "C" int gsc_device_count(void) {
+    FpGuard g;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok == n ? n : 0;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return GSC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return set_err(GSC_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return GSC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {  // pinned staging
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return GSC_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return set_err(GSC_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return GSC_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+enum { EV_COUNT = 9 };
+
+struct gsc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    gsc_stats stats = {};
+    // batch state
+    std::vector<GscFrame> h_frames;
+    int F = 0, Kmax = 0, cs = 4, bits = 8, maxN = 0;
+    long long sumN = 0;
+    long long pcm_samples = 0;
+    // device buffers
+    DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
+        sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
+        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc;
+    HostBuf hpcm, hout;
+    bool attr_set[4] = {false, false, false, false};
+};
+
+static std::atomic<int> g_rr{0};
+static std::mutex g_trig_mu;
+static bool g_trig_done[16] = {};
+
+static void fill_trig(GscTrig &t, int cs) {
+    const double pi = 3.14159265358979323846;
+    memset(&t, 0, sizeof(t));
+    for (int k = 0; k < cs; ++k)
+        for (int n = 0; n < cs; ++n) {
+            t.dct[k * cs + n] = cos(pi / (double)cs * ((double)n + 0.5) * (double)k);  // enc:1712
+            t.dc[k * cs + n] = cos(-2.0 * pi * (double)k * (double)n / (double)cs);    // enc:270
+            t.ds[k * cs + n] = sin(-2.0 * pi * (double)k * (double)n / (double)cs);    // enc:271
+            t.ic[k * cs + n] = cos(2.0 * pi * (double)k * (double)n / (double)cs);     // enc:292
+            t.is[k * cs + n] = sin(2.0 * pi * (double)k * (double)n / (double)cs);     // enc:293
+        }
+    t.s0 = sqrt(0.5);
+    t.scale = sqrt(2.0 / (double)cs);
+}
+
+static int upload_trig(int device) {
+    std::lock_guard<std::mutex> lk(g_trig_mu);
+    if (device < 16 && g_trig_done[device]) return GSC_OK;
+    GscTrig t[3];
+    fill_trig(t[0], 2); fill_trig(t[1], 4); fill_trig(t[2], 8);
+    CU(cudaMemcpyToSymbol(c_trig_all, t, sizeof(t)));
+    if (device < 16) g_trig_done[device] = true;
+    return GSC_OK;
+}
+
+extern "C" gsc_ctx *gsc_create(int device) {
+    FpGuard g;
+    int n = gsc_device_count();
+    if (n <= 0) { set_err(GSC_ERR_NODEVICE, "no usable sm_100 CUDA device (libgsc_cuda has no CPU fallback)"); return nullptr; }
+    if (device < 0) device = g_rr.fetch_add(1) % n;
+    if (device >= n) { set_err(GSC_ERR_ARG, "device %d out of range (%d devices)", device, n); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(GSC_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+    gsc_ctx *c = new (std::nothrow) gsc_ctx();
+    if (!c) { set_err(GSC_ERR_CUDA, "out of host memory"); return nullptr; }
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_err(GSC_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+    if (upload_trig(device) != GSC_OK) { gsc_destroy(c); return nullptr; }
+    return c;
+}
+
+extern "C" void gsc_destroy(gsc_ctx *c) {
+    if (!c) return;
+    FpGuard g;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->frames, &c->pcm, &c->divider, &c->vout, &c->attr, &c->atten, &c->feat, &c->dst,
+                      &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
+                      &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
+                      &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
+                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc};
+    for (DevBuf *b : bufs) b->release();
+    c->hpcm.release();
+    c->hout.release();
+    for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int gsc_ctx_device(const gsc_ctx *c) { return c ? c->device : -1; }
+extern "C" void *gsc_ctx_stream(const gsc_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int gsc_synchronize(gsc_ctx *c) {
+    if (!c) return set_err(GSC_ERR_ARG, "null context");
+    FpGuard g;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return GSC_OK;
+}
+extern "C" int gsc_get_stats(gsc_ctx *c, gsc_stats *out) {
+    if (!c || !out) return set_err(GSC_ERR_ARG, "null argument");
+    *out = c->stats;
+    return GSC_OK;
+}
+extern "C" int gsc_reset_stats(gsc_ctx *c) {
+    if (!c) return set_err(GSC_ERR_ARG, "null context");
+    memset(&c->stats, 0, sizeof(c->stats));
+    return GSC_OK;
+}
+
+extern "C" void gsc_default_params(gsc_params *p) {
+    p->chunk_size = 4;
+    p->chunk_bit_depth = 8;
+    p->chunks_per_frame = GSC_MAX_K;
+    p->precision = 3;
+    p->max_passes = 100;
+    p->kmeans_mode = 0;
+    p->lloyd_iters = 30;
+    p->reserved = 0;
+}
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                                              \
+    do {                                                                                       \
+        kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);                               \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess)                                                                 \
+            return set_err(GSC_ERR_CUDA, "launch %s failed: %s", #kern, cudaGetErrorString(e_)); \
+        (ctx)->stats.kernel_launches++;                                                        \
+    } while (0)
+
+#define SMEM_OPTIN(kern, bytes)                                                                 \
+    do {                                                                                        \
+        if ((bytes) > 48 * 1024)                                                                \
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+    } while (0)
+
+static int h2d(gsc_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return GSC_OK;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += bytes;
+    return GSC_OK;
+}
+static int d2h(gsc_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!bytes) return GSC_OK;
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += bytes;
+    return GSC_OK;
+}
+#define TRY(x) do { int rc_ = (x); if (rc_ != GSC_OK) return rc_; } while (0)
+
+static bool cs_ok(int cs) { return cs == 2 || cs == 4 || cs == 8; }
+static int check_common(gsc_ctx *c, int cs, int bits) {
+    if (!c) return set_err(GSC_ERR_ARG, "null context");
+    if (!cs_ok(cs)) return set_err(GSC_ERR_UNSUPPORTED, "chunk size %d unsupported (2, 4, 8)", cs);
+    if (bits < 2 || bits > 16) return set_err(GSC_ERR_ARG, "chunk bit depth %d out of range", bits);
+    CU(cudaSetDevice(c->device));
+    return GSC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batch plan
+// ---------------------------------------------------------------------------
+// Fills ctx->h_frames from descriptors; pcm offsets are relative to `pcm_base`
+// when pointers are device pointers, or packed when staging from host.
+static int plan_batch(gsc_ctx *c, const gsc_frame_desc *fr, int F, int cs, int K, int precision,
+                      bool pack, const int16_t *dev_base) {
+    c->h_frames.resize(F);
+    long long off = 0, pcm_off = 0;
+    int maxN = 0;
+    for (int i = 0; i < F; ++i) {
+        if (fr[i].channels <= 0 || fr[i].samples <= 0 || !fr[i].pcm)
+            return set_err(GSC_ERR_ARG, "frame %d: bad descriptor", i);
+        GscFrame &g = c->h_frames[i];
+        g.C = fr[i].channels;
+        g.S = fr[i].samples;
+        g.cc = (g.S - 1) / cs + 1;  // enc:455
+        g.N = g.cc * g.C;
+        g.chunk_off = off;
+        g.slot = i;
+        g.pad = 0;
+        if (precision > 0 && g.N > K) { g.K = K; g.R = K; }         // enc:808
+        else if (g.N <= K) { g.K = 0; g.R = g.N; }                  // enc:891-912
+        else return set_err(GSC_ERR_UNSUPPORTED, "frame %d: passthrough needs N <= chunks_per_frame", i);
+        if (pack) { g.pcm_off = pcm_off; g.stride = g.S; pcm_off += (long long)g.C * g.S; }
+        else { g.pcm_off = fr[i].pcm - dev_base; g.stride = fr[i].stride; }
+        off += g.N;
+        if (g.N > maxN) maxN = g.N;
+    }
+    c->F = F; c->sumN = off; c->maxN = maxN; c->Kmax = K; c->cs = cs; c->pcm_samples = pcm_off;
+    return GSC_OK;
+}
+
+static int upload_frames(gsc_ctx *c) {
+    TRY(c->frames.ensure(sizeof(GscFrame) * c->F));
+    return h2d(c, c->frames.p, c->h_frames.data(), sizeof(GscFrame) * c->F);
+}
+
+// ---------------------------------------------------------------------------
+// stage launchers (all operate on the current batch of ctx)
+// ---------------------------------------------------------------------------
+#define DISPATCH_CS(cs, CALL)                 \
+    do {                                      \
+        switch (cs) {                         \
+            case 2: { constexpr int CS = 2; CALL; } break; \
+            case 4: { constexpr int CS = 4; CALL; } break; \
+            case 8: { constexpr int CS = 8; CALL; } break; \
+            default: return set_err(GSC_ERR_UNSUPPORTED, "chunk size %d", cs); \
+        }                                     \
+    } while (0)
+
+static int stage_divider(gsc_ctx *c, bool want_v) {
+    TRY(c->divider.ensure(sizeof(int) * c->F));
+    if (want_v) TRY(c->vout.ensure(sizeof(double) * 64 * c->F));
+    DISPATCH_CS(c->cs, LAUNCH(c, k_find_divider<CS>, c->F, 64, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
+                              c->bits, c->divider.as<int>(), want_v ? c->vout.as<double>() : nullptr));
+    return GSC_OK;
+}
+
+static int stage_chunks(gsc_ctx *c, bool want_atten, bool want_dst, bool want_feat) {
+    const int cs = c->cs;
+    TRY(c->attr.ensure((size_t)c->sumN));
+    if (want_atten) TRY(c->atten.ensure((size_t)c->sumN));
+    if (want_dst) TRY(c->dst.ensure(sizeof(short) * (size_t)c->sumN * cs));
+    if (want_feat) TRY(c->feat.ensure(sizeof(float) * (size_t)c->sumN * 2 * cs));
+    dim3 grid((c->maxN + 255) / 256, c->F);
+    DISPATCH_CS(cs, LAUNCH(c, k_make_chunks<CS>, grid, 256, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(), c->bits,
+                           c->divider.as<int>(), c->attr.as<unsigned char>(),
+                           want_atten ? c->atten.as<unsigned char>() : nullptr,
+                           want_feat ? c->feat.as<float>() : nullptr, want_dst ? c->dst.as<short>() : nullptr));
+    return GSC_OK;
+}
+
+#define DISPATCH_D(D_, CALL)                  \
+    do {                                      \
+        switch (D_) {                         \
+            case 4: { constexpr int D = 4; CALL; } break;  \
+            case 8: { constexpr int D = 8; CALL; } break;  \
+            case 16: { constexpr int D = 16; CALL; } break; \
+            default: return set_err(GSC_ERR_UNSUPPORTED, "feature dimension %d unsupported (4, 8, 16)", D_); \
+        }                                     \
+    } while (0)
+
+template <int D>
+static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
+    size_t smem = (size_t)((c->maxN + 31) / 32) * 4;
+    if (smem > 200 * 1024) return set_err(GSC_ERR_UNSUPPORTED, "frame too large for the seeding kernel");
+    SMEM_OPTIN(k_seed<D>, smem);
+    LAUNCH(c, k_seed<D>, c->F, GSC_SEED_THREADS, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), init_type,
+           c->pnorm.as<float>(), c->up.as<float>(), c->r.as<float>(), c->sid.as<int>(),
+           want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax);
+    return GSC_OK;
+}
+
+// seeding + one mean update over the seed cells (yakmo init() + first half of run())
+static int stage_seed(gsc_ctx *c, int D, int init_type, bool want_seeds) {
+    const size_t n = (size_t)c->sumN, fk = (size_t)c->F * c->Kmax;
+    TRY(c->pnorm.ensure(4 * n)); TRY(c->up.ensure(4 * n)); TRY(c->r.ensure(4 * n)); TRY(c->sid.ensure(4 * n));
+    TRY(c->cen.ensure(4 * fk * D)); TRY(c->cnorm.ensure(4 * fk)); TRY(c->sums.ensure(4 * fk * D));
+    TRY(c->cnt0.ensure(4 * fk));
+    if (want_seeds) TRY(c->seeds.ensure(4 * fk));
+    DISPATCH_D(D, TRY(seed_launch<D>(c, init_type, want_seeds)));
+    dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
+    DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
+                         c->sid.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), c->Kmax));
+    dim3 g3((c->Kmax + 255) / 256, c->F);
+    DISPATCH_D(D, LAUNCH(c, k_means_from_sums<D>, g3, 256, 0, c->frames.as<GscFrame>(), c->sums.as<float>(),
+                         c->cnt0.as<int>(), c->cen.as<float>(), c->Kmax, 0));
+    return GSC_OK;
+}
+
+static int stage_assign(gsc_ctx *c, int D, bool want_dist) {
+    TRY(c->labels.ensure(4 * (size_t)c->sumN));
+    if (want_dist) TRY(c->dist.ensure(4 * (size_t)c->sumN));
+    dim3 grid((c->maxN + 128 * GSC_ASSIGN_P - 1) / (128 * GSC_ASSIGN_P), c->F);
+    DISPATCH_D(D, LAUNCH(c, k_assign<D>, grid, 128, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
+                         c->labels.as<int>(), want_dist ? c->dist.as<float>() : nullptr, c->Kmax));
+    return GSC_OK;
+}
+
+static int stage_lloyd_update(gsc_ctx *c, int D) {
+    const size_t fk = (size_t)c->F * c->Kmax;
+    TRY(c->sums.ensure(4 * fk * D)); TRY(c->cnt0.ensure(4 * fk));
+    dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
+    DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
+                         c->labels.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), c->Kmax));
+    dim3 g3((c->Kmax + 255) / 256, c->F);
+    DISPATCH_D(D, LAUNCH(c, k_means_from_sums<D>, g3, 256, 0, c->frames.as<GscFrame>(), c->sums.as<float>(),
+                         c->cnt0.as<int>(), c->cen.as<float>(), c->Kmax, 1));
+    return GSC_OK;
+}
+
+template <int D, int CPT>
+static int online_launch(gsc_ctx *c, double tol, int max_passes, int force_exact) {
+    size_t smem = sizeof(GscOnlineSmem<D>) + sizeof(int) * 2 * GSC_ON_T * CPT;
+    auto k_online_inst = k_online<D, CPT>;
+    SMEM_OPTIN(k_online_inst, smem);
+    LAUNCH(c, k_online_inst, c->F, GSC_ON_T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
+           c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, force_exact);
+    return GSC_OK;
+}
+
+static double int_power10_neg(int prec) {  // IntPower(10.0, -Precision), enc:761
+    double p = 1.0;
+    for (int i = 0; i < prec; ++i) p *= 10.0;
+    return 1.0 / p;
+}
+
+static int g_force_exact = -1;
+// Debug hook (tests): 1 = score every centroid exactly in the online kernel
+// instead of using the lower-bound filter; results must be identical.
+extern "C" void gsc_debug_set_online_exact(int on) { g_force_exact = on ? 1 : 0; }
+static int force_exact_flag() {
+    if (g_force_exact < 0) {
+        const char *e = getenv("GSC_ONLINE_EXACT");
+        g_force_exact = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_force_exact;
+}
+
+// online k-means; labels buffer must already hold per-point guesses
+static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
+    TRY(c->passes.ensure(4 * (size_t)c->F)); TRY(c->err.ensure(8 * (size_t)c->F));
+    CU(cudaMemsetAsync(c->passes.p, 0, 4 * (size_t)c->F, c->stream));
+    CU(cudaMemsetAsync(c->err.p, 0, 8 * (size_t)c->F, c->stream));
+    const double tol = int_power10_neg(precision);
+    const int K = c->Kmax, fe = force_exact_flag();
+    if (D == 8) {
+        if (K <= 512) return online_launch<8, 1>(c, tol, max_passes, fe);
+        if (K <= 1024) return online_launch<8, 2>(c, tol, max_passes, fe);
+        if (K <= 2048) return online_launch<8, 4>(c, tol, max_passes, fe);
+        if (K <= 4096) return online_launch<8, 8>(c, tol, max_passes, fe);
+    } else if (D == 4) {
+        if (K <= 512) return online_launch<4, 1>(c, tol, max_passes, fe);
+        if (K <= 1024) return online_launch<4, 2>(c, tol, max_passes, fe);
+        if (K <= 2048) return online_launch<4, 4>(c, tol, max_passes, fe);
+        if (K <= 4096) return online_launch<4, 8>(c, tol, max_passes, fe);
+    }
+    return set_err(GSC_ERR_UNSUPPORTED, "online k-means supports D in {4, 8} and K <= 4096 (got D=%d K=%d)", D, K);
+}
+
+static int stage_dictionary(gsc_ctx *c, bool want_entry) {
+    const int cs = c->cs;
+    const size_t fk = (size_t)c->F * c->Kmax;
+    TRY(c->means0.ensure(4 * fk * cs)); TRY(c->cnt0.ensure(4 * fk)); TRY(c->means.ensure(4 * fk * cs));
+    TRY(c->order.ensure(4 * fk)); TRY(c->counts.ensure(4 * fk)); TRY(c->dict.ensure(2 * fk * cs));
+    TRY(c->datten.ensure(fk)); TRY(c->dattr.ensure(fk));
+    if (want_entry) TRY(c->entry.ensure(4 * (size_t)c->sumN));
+    dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
+    DISPATCH_CS(cs, LAUNCH(c, k_class_means<CS>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
+                           c->attr.as<unsigned char>(), c->labels.as<int>(), c->means0.as<float>(), c->cnt0.as<int>(),
+                           c->Kmax));
+    size_t smem = sizeof(int) * 4 * (size_t)c->Kmax;
+    DISPATCH_CS(cs, {
+        SMEM_OPTIN(k_dictionary<CS>, smem);
+        LAUNCH(c, k_dictionary<CS>, c->F, 256, smem, c->frames.as<GscFrame>(), c->pcm.as<short>(), c->bits,
+               c->divider.as<int>(), c->means0.as<float>(), c->cnt0.as<int>(), c->means.as<float>(), c->order.as<int>(),
+               c->counts.as<int>(), c->dict.as<short>(), c->datten.as<unsigned char>(), c->dattr.as<unsigned char>(),
+               want_entry ? c->entry.as<int>() : nullptr, c->labels.as<int>(), c->Kmax);
+    });
+    return GSC_OK;
+}
+
+static int stage_knnfit(gsc_ctx *c, bool want_band) {
+    const int cs = c->cs;
+    const size_t fk = (size_t)c->F * c->Kmax;
+    TRY(c->best.ensure(4 * (size_t)c->sumN)); TRY(c->use.ensure(4 * fk)); TRY(c->overfull.ensure(4 * (size_t)c->F));
+    if (want_band) TRY(c->band.ensure(4 * (size_t)c->sumN));
+    CU(cudaMemsetAsync(c->use.p, 0, 4 * fk, c->stream));
+    CU(cudaMemsetAsync(c->overfull.p, 0, 4 * (size_t)c->F, c->stream));
+    dim3 grid((c->maxN + 255) / 256, c->F);
+    size_t smem = sizeof(float) * (size_t)c->Kmax * cs;
+    DISPATCH_CS(cs, {
+        SMEM_OPTIN(k_knnfit<CS>, smem);
+        LAUNCH(c, k_knnfit<CS>, grid, 256, smem, c->frames.as<GscFrame>(), c->pcm.as<short>(), c->bits,
+               c->divider.as<int>(), c->dict.as<short>(), c->datten.as<unsigned char>(), c->best.as<int>(),
+               c->use.as<int>(), want_band ? c->band.as<int>() : nullptr, c->overfull.as<int>(), c->Kmax);
+    });
+    return GSC_OK;
+}
+
+static int stage_finalize(gsc_ctx *c, bool full) {
+    const int cs = c->cs;
+    const size_t fk = (size_t)c->F * c->Kmax;
+    TRY(c->remap.ensure(4 * fk)); TRY(c->order2.ensure(4 * fk)); TRY(c->newR.ensure(4 * (size_t)c->F));
+    if (full) {
+        TRY(c->odict.ensure(2 * fk * cs)); TRY(c->odatten.ensure(fk));
+        TRY(c->oindex.ensure(4 * (size_t)c->sumN)); TRY(c->oattr.ensure((size_t)c->sumN));
+    }
+    size_t smem = sizeof(int) * 4 * (size_t)c->Kmax;
+    DISPATCH_CS(cs, {
+        SMEM_OPTIN(k_finalize<CS>, smem);
+        LAUNCH(c, k_finalize<CS>, c->F, 256, smem, c->frames.as<GscFrame>(), c->use.as<int>(),
+               full ? c->dict.as<short>() : nullptr, full ? c->datten.as<unsigned char>() : nullptr,
+               full ? c->best.as<int>() : nullptr, c->remap.as<int>(), c->order2.as<int>(), c->newR.as<int>(),
+               full ? c->odict.as<short>() : nullptr, full ? c->odatten.as<unsigned char>() : nullptr,
+               full ? c->oindex.as<int>() : nullptr, full ? c->oattr.as<unsigned char>() : nullptr, c->Kmax);
+    });
+    return GSC_OK;
+}
+
+// Upload a single frame's planar PCM (packed rows) as a one-frame batch.
+static int single_frame_pcm(gsc_ctx *c, const int16_t *pcm, int64_t stride, int C, int S, int cs, int bits, int K,
+                            int precision) {
+    if (!pcm || C <= 0 || S <= 0) return set_err(GSC_ERR_ARG, "bad pcm arguments");
+    gsc_frame_desc d = {pcm, stride, C, S};
+    c->bits = bits;
+    TRY(plan_batch(c, &d, 1, cs, K, precision, true, nullptr));
+    TRY(c->hpcm.ensure(2 * (size_t)C * S));
+    for (int j = 0; j < C; ++j) memcpy(c->hpcm.as<int16_t>() + (size_t)j * S, pcm + (size_t)j * stride, 2 * (size_t)S);
+    TRY(c->pcm.ensure(2 * (size_t)C * S));
+    TRY(h2d(c, c->pcm.p, c->hpcm.p, 2 * (size_t)C * S));
+    return upload_frames(c);
+}
+
+// One-frame batch for feature-space calls (no PCM).
+static int single_frame_points(gsc_ctx *c, int N, int K) {
+    c->h_frames.resize(1);
+    GscFrame &g = c->h_frames[0];
+    memset(&g, 0, sizeof(g));
+    g.C = 1; g.S = N; g.cc = N; g.N = N; g.K = K; g.R = K; g.slot = 0;
+    c->F = 1; c->sumN = N; c->maxN = N; c->Kmax = K;
+    return upload_frames(c);
+}
+
+static int sync(gsc_ctx *c) {
+    CU(cudaStreamSynchronize(c->stream));
+    return GSC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 2. batched per-frame stages
+// ---------------------------------------------------------------------------
+extern "C" int gsc_find_attenuation_divider(gsc_ctx *c, const int16_t *pcm, int64_t stride, int C, int S, int cs,
+                                            int bits, int *divider_out, double *v_out) {
+    FpGuard g;
+    TRY(check_common(c, cs, bits));
+    TRY(single_frame_pcm(c, pcm, stride, C, S, cs, bits, GSC_MAX_K, 1));
+    TRY(stage_divider(c, v_out != nullptr));
+    int div = 0;
+    TRY(d2h(c, &div, c->divider.p, sizeof(int)));
+    if (v_out) TRY(d2h(c, v_out, c->vout.p, sizeof(double) * 64));
+    TRY(sync(c));
+    if (divider_out) *divider_out = div;
+    return GSC_OK;
+}
+
+extern "C" int gsc_make_chunks(gsc_ctx *c, const int16_t *pcm, int64_t stride, int C, int S, int cs, int bits,
+                               int divider, uint8_t *attr, uint8_t *atten, float *feat, int16_t *dst) {
+    FpGuard g;
+    TRY(check_common(c, cs, bits));
+    if (divider < 1) return set_err(GSC_ERR_ARG, "divider must be >= 1");
+    TRY(single_frame_pcm(c, pcm, stride, C, S, cs, bits, GSC_MAX_K, 1));
+    TRY(c->divider.ensure(sizeof(int)));
+    TRY(h2d(c, c->divider.p, &divider, sizeof(int)));
+    TRY(stage_chunks(c, atten != nullptr, dst != nullptr, feat != nullptr));
+    const size_t N = (size_t)c->sumN;
+    if (attr) TRY(d2h(c, attr, c->attr.p, N));
+    if (atten) TRY(d2h(c, atten, c->atten.p, N));
+    if (feat) TRY(d2h(c, feat, c->feat.p, 4 * N * 2 * cs));
+    if (dst) TRY(d2h(c, dst, c->dst.p, 2 * N * cs));
+    return sync(c);
+}
+
+static int upload_points(gsc_ctx *c, const float *X, int N, int D, int K) {
+    if (!X || N <= 0 || K <= 0 || K > GSC_MAX_K) return set_err(GSC_ERR_ARG, "bad arguments (N=%d K=%d)", N, K);
+    CU(cudaSetDevice(c->device));
+    TRY(single_frame_points(c, N, K));
+    TRY(c->feat.ensure(4 * (size_t)N * D));
+    return h2d(c, c->feat.p, X, 4 * (size_t)N * D);
+}
+
+template <int D>
+static int yakmo_reassign_launch(gsc_ctx *c) {
+    dim3 grid((c->maxN + 127) / 128, c->F);
+    LAUNCH(c, k_assign_yakmo<D>, grid, 128, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->pnorm.as<float>(),
+           c->cen.as<float>(), c->labels.as<int>(), c->Kmax);
+    return GSC_OK;
+}
+
+extern "C" int gsc_yakmo(gsc_ctx *c, const float *X, int N, int D, int K, int init_type, int max_iter, float *centroids,
+                         int32_t *labels, int32_t *seeds) {
+    FpGuard g;
+    if (!c) return set_err(GSC_ERR_ARG, "null context");
+    if (K > N) return set_err(GSC_ERR_ARG, "k (%d) > rows (%d)", K, N);
+    TRY(upload_points(c, X, N, D, K));
+    TRY(stage_seed(c, D, init_type, seeds != nullptr));
+    TRY(c->labels.ensure(4 * (size_t)N));
+    // run(): labels start as the seed cells, then reassign after each mean update
+    CU(cudaMemcpyAsync(c->labels.p, c->sid.p, 4 * (size_t)N, cudaMemcpyDeviceToDevice, c->stream));
+    if (labels || max_iter > 0) {
+        std::vector<int> prev, cur;
+        for (int it = 0; it <= max_iter; ++it) {
+            if (it > 0) {  // mean update from the current assignment (NaN for empty cells, like run())
+                const size_t fk = (size_t)c->F * c->Kmax;
+                (void)fk;
+                dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
+                DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(),
+                                     c->feat.as<float>(), c->labels.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(),
+                                     c->Kmax));
+                dim3 g3((c->Kmax + 255) / 256, c->F);
+                DISPATCH_D(D, LAUNCH(c, k_means_from_sums<D>, g3, 256, 0, c->frames.as<GscFrame>(), c->sums.as<float>(),
+                                     c->cnt0.as<int>(), c->cen.as<float>(), c->Kmax, 0));
+            }
+            DISPATCH_D(D, TRY(yakmo_reassign_launch<D>(c)));
+            if (max_iter > 0) {  // moved == 0 -> stop
+                cur.resize(N);
+                TRY(d2h(c, cur.data(), c->labels.p, 4 * (size_t)N));
+                TRY(sync(c));
+                if (!prev.empty() && prev == cur) break;
+                prev = cur;
+            }
+        }
+    }
+    if (centroids) TRY(d2h(c, centroids, c->cen.p, 4 * (size_t)K * D));
+    if (labels) TRY(d2h(c, labels, c->labels.p, 4 * (size_t)N));
+    if (seeds) TRY(d2h(c, seeds, c->seeds.p, 4 * (size_t)K));
+    return sync(c);
+}
+
+extern "C" int gsc_assign(gsc_ctx *c, const float *X, int N, int D, const float *centroids, int K, int32_t *labels,
+                          float *dist) {
+    FpGuard g;
+    if (!c || !centroids || !labels) return set_err(GSC_ERR_ARG, "null argument");
+    TRY(upload_points(c, X, N, D, K));
+    TRY(c->cen.ensure(4 * (size_t)K * D));
+    TRY(h2d(c, c->cen.p, centroids, 4 * (size_t)K * D));
+    TRY(stage_assign(c, D, dist != nullptr));
+    TRY(d2h(c, labels, c->labels.p, 4 * (size_t)N));
+    if (dist) TRY(d2h(c, dist, c->dist.p, 4 * (size_t)N));
+    return sync(c);
+}
+
+extern "C" int gsc_knn_scan_reduce(gsc_ctx *c, const float *X, int N, int D, float *centroids, int K, int precision,
+                                   int max_passes, int32_t *labels, int *passes, double *err) {
+    FpGuard g;
+    if (!c || !centroids) return set_err(GSC_ERR_ARG, "null argument");
+    if (max_passes < 1) return set_err(GSC_ERR_ARG, "max_passes must be >= 1");
+    TRY(upload_points(c, X, N, D, K));
+    TRY(c->cen.ensure(4 * (size_t)K * D));
+    TRY(h2d(c, c->cen.p, centroids, 4 * (size_t)K * D));
+    TRY(stage_assign(c, D, false));  // guesses for the first pass
+    TRY(stage_online(c, D, precision, max_passes));
+    TRY(d2h(c, centroids, c->cen.p, 4 * (size_t)K * D));
+    if (labels) TRY(d2h(c, labels, c->labels.p, 4 * (size_t)N));
+    int p = 0; double e = 0;
+    TRY(d2h(c, &p, c->passes.p, 4)); TRY(d2h(c, &e, c->err.p, 8));
+    TRY(sync(c));
+    if (passes) *passes = p;
+    if (err) *err = e;
+    return GSC_OK;
+}
+
+extern "C" int gsc_lloyd(gsc_ctx *c, const float *X, int N, int D, float *centroids, int K, int iters,
+                         int32_t *labels) {
+    FpGuard g;
+    if (!c || !centroids) return set_err(GSC_ERR_ARG, "null argument");
+    TRY(upload_points(c, X, N, D, K));
+    TRY(c->cen.ensure(4 * (size_t)K * D));
+    TRY(h2d(c, c->cen.p, centroids, 4 * (size_t)K * D));
+    for (int it = 0; it < iters; ++it) {
+        TRY(stage_assign(c, D, false));
+        TRY(stage_lloyd_update(c, D));
+    }
+    TRY(stage_assign(c, D, false));
+    TRY(d2h(c, centroids, c->cen.p, 4 * (size_t)K * D));
+    if (labels) TRY(d2h(c, labels, c->labels.p, 4 * (size_t)N));
+    return sync(c);
+}
+
+extern "C" int gsc_build_dictionary(gsc_ctx *c, const int32_t *labels, const int16_t *pcm, int64_t stride, int C, int S,
+                                    const uint8_t *attr, int cs, int K, int bits, int divider, float *means,
+                                    int32_t *order, int32_t *counts, int16_t *dict, uint8_t *datten, uint8_t *dattr,
+                                    int32_t *entry) {
+    FpGuard g;
+    TRY(check_common(c, cs, bits));
+    if (!labels || !attr || K <= 0 || K > GSC_MAX_K || divider < 1) return set_err(GSC_ERR_ARG, "bad arguments");
+    TRY(single_frame_pcm(c, pcm, stride, C, S, cs, bits, K, 1));
+    GscFrame &f = c->h_frames[0];
+    f.K = K; f.R = K;  // caller asked for a K-entry dictionary regardless of N
+    TRY(upload_frames(c));
+    const size_t N = (size_t)c->sumN;
+    TRY(c->labels.ensure(4 * N)); TRY(c->attr.ensure(N)); TRY(c->divider.ensure(4));
+    TRY(h2d(c, c->labels.p, labels, 4 * N));
+    TRY(h2d(c, c->attr.p, attr, N));
+    TRY(h2d(c, c->divider.p, &divider, 4));
+    TRY(stage_dictionary(c, entry != nullptr));
+    const size_t k = (size_t)K;
+    if (means) TRY(d2h(c, means, c->means.p, 4 * k * cs));
+    if (order) TRY(d2h(c, order, c->order.p, 4 * k));
+    if (counts) TRY(d2h(c, counts, c->counts.p, 4 * k));
+    if (dict) TRY(d2h(c, dict, c->dict.p, 2 * k * cs));
+    if (datten) TRY(d2h(c, datten, c->datten.p, k));
+    if (dattr) TRY(d2h(c, dattr, c->dattr.p, k));
+    if (entry) TRY(d2h(c, entry, c->entry.p, 4 * N));
+    return sync(c);
+}
+
+extern "C" int gsc_knnfit(gsc_ctx *c, const int16_t *dict, const uint8_t *datten, int R, int cs, int bits, int divider,
+                          const int16_t *pcm, int64_t stride, int C, int S, int32_t *best, int32_t *use,
+                          int32_t *band) {
+    FpGuard g;
+    TRY(check_common(c, cs, bits));
+    if (!dict || !datten || R <= 0 || R > GSC_MAX_K || divider < 1) return set_err(GSC_ERR_ARG, "bad arguments");
+    TRY(single_frame_pcm(c, pcm, stride, C, S, cs, bits, R, 1));
+    GscFrame &f = c->h_frames[0];
+    f.K = R; f.R = R;
+    c->Kmax = R;
+    TRY(upload_frames(c));
+    TRY(c->dict.ensure(2 * (size_t)R * cs)); TRY(c->datten.ensure(R)); TRY(c->divider.ensure(4));
+    TRY(h2d(c, c->dict.p, dict, 2 * (size_t)R * cs));
+    TRY(h2d(c, c->datten.p, datten, R));
+    TRY(h2d(c, c->divider.p, &divider, 4));
+    TRY(stage_knnfit(c, band != nullptr));
+    const size_t N = (size_t)c->sumN;
+    if (best) TRY(d2h(c, best, c->best.p, 4 * N));
+    if (use) TRY(d2h(c, use, c->use.p, 4 * (size_t)R));
+    if (band) TRY(d2h(c, band, c->band.p, 4 * N));
+    return sync(c);
+}
+
+extern "C" int gsc_finalize_dictionary(gsc_ctx *c, const int32_t *use, int R, int32_t *remap, int32_t *order,
+                                       int *new_R) {
+    FpGuard g;
+    if (!c || !use || R <= 0 || R > GSC_MAX_K) return set_err(GSC_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    c->cs = 4;
+    TRY(single_frame_points(c, 1, R));
+    TRY(c->use.ensure(4 * (size_t)R));
+    TRY(h2d(c, c->use.p, use, 4 * (size_t)R));
+    TRY(stage_finalize(c, false));
+    int n = 0;
+    if (remap) TRY(d2h(c, remap, c->remap.p, 4 * (size_t)R));
+    if (order) TRY(d2h(c, order, c->order2.p, 4 * (size_t)R));
+    TRY(d2h(c, &n, c->newR.p, 4));
+    TRY(sync(c));
+    if (new_R) *new_R = n;
+    return GSC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 3. whole frames
+// ---------------------------------------------------------------------------
+extern "C" int gsc_dict_capacity(const gsc_params *p, int channels, int samples) {
+    (void)channels; (void)samples;
+    return p ? p->chunks_per_frame : GSC_MAX_K;
+}
+
+static int check_params(const gsc_params *p) {
+    if (!p) return set_err(GSC_ERR_ARG, "null params");
+    if (!cs_ok(p->chunk_size)) return set_err(GSC_ERR_UNSUPPORTED, "chunk size %d unsupported", p->chunk_size);
+    if (p->chunks_per_frame < 1 || p->chunks_per_frame > GSC_MAX_K)
+        return set_err(GSC_ERR_ARG, "chunks_per_frame %d out of range", p->chunks_per_frame);
+    if (p->chunk_bit_depth != 8 && p->chunk_bit_depth != 12)
+        return set_err(GSC_ERR_ARG, "chunk_bit_depth must be 8 or 12 (enc:1041)");
+    if (p->max_passes < 1) return set_err(GSC_ERR_ARG, "max_passes must be >= 1");
+    return GSC_OK;
+}
+
+// DoFrame (enc:1433-1447) for the current batch; PCM already on the device.
+static int run_pipeline(gsc_ctx *c, const gsc_params *P) {
+    const int D = 2 * P->chunk_size;
+    c->bits = P->chunk_bit_depth;
+    bool any_reduce = false;
+    for (const GscFrame &f : c->h_frames) any_reduce |= f.K > 0;
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    TRY(stage_divider(c, false));                                   // enc:1440
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    TRY(stage_chunks(c, false, false, true));                       // enc:1441
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    TRY(c->labels.ensure(4 * (size_t)c->sumN));
+    if (any_reduce) TRY(stage_seed(c, D, 1, false));                // enc:824-828
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    if (any_reduce) {
+        if (P->kmeans_mode == 1) {
+            for (int it = 0; it < P->lloyd_iters; ++it) { TRY(stage_assign(c, D, false)); TRY(stage_lloyd_update(c, D)); }
+            TRY(stage_assign(c, D, false));
+            TRY(c->passes.ensure(4 * (size_t)c->F)); TRY(c->err.ensure(8 * (size_t)c->F));
+            CU(cudaMemsetAsync(c->passes.p, 0, 4 * (size_t)c->F, c->stream));
+            CU(cudaMemsetAsync(c->err.p, 0, 8 * (size_t)c->F, c->stream));
+        } else {
+            // first-pass guesses: the seed cell of every point
+            CU(cudaMemcpyAsync(c->labels.p, c->sid.p, 4 * (size_t)c->sumN, cudaMemcpyDeviceToDevice, c->stream));
+            TRY(stage_online(c, D, P->precision, P->max_passes));   // enc:835
+        }
+    } else {
+        TRY(c->passes.ensure(4 * (size_t)c->F)); TRY(c->err.ensure(8 * (size_t)c->F));
+        CU(cudaMemsetAsync(c->passes.p, 0, 4 * (size_t)c->F, c->stream));
+        CU(cudaMemsetAsync(c->err.p, 0, 8 * (size_t)c->F, c->stream));
+    }
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    TRY(stage_dictionary(c, false));                                // enc:843-889
+    CU(cudaEventRecord(c->ev[5], c->stream));
+    TRY(stage_knnfit(c, false));                                    // enc:1443
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    TRY(stage_finalize(c, true));                                   // enc:970-977
+    CU(cudaEventRecord(c->ev[7], c->stream));
+    return GSC_OK;
+}
+
+static int collect_stage_times(gsc_ctx *c) {
+    for (int i = 0; i < 7; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]) == cudaSuccess) c->stats.last_stage_ms[i] = ms;
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]) == cudaSuccess) c->stats.last_stage_ms[7] = ms;
+    cudaGetLastError();
+    return GSC_OK;
+}
+
+extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
+    FpGuard g;
+    if (!c || !res || n_frames != c->F) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_results");
+    CU(cudaSetDevice(c->device));
+    const int F = c->F, cs = c->cs, Kmax = c->Kmax;
+    // small per-frame scalars
+    std::vector<int> divider(F), passes(F), newR(F), overfull(F);
+    std::vector<double> err(F);
+    TRY(d2h(c, divider.data(), c->divider.p, 4 * (size_t)F));
+    TRY(d2h(c, passes.data(), c->passes.p, 4 * (size_t)F));
+    TRY(d2h(c, newR.data(), c->newR.p, 4 * (size_t)F));
+    TRY(d2h(c, overfull.data(), c->overfull.p, 4 * (size_t)F));
+    TRY(d2h(c, err.data(), c->err.p, 8 * (size_t)F));
+    // bulk outputs through pinned staging
+    const size_t nN = (size_t)c->sumN, fk = (size_t)F * Kmax;
+    const size_t o_index = 0, o_attr = o_index + 4 * nN, o_dict = (o_attr + nN + 15) & ~(size_t)15,
+                 o_datten = o_dict + 2 * fk * cs, total = o_datten + fk;
+    TRY(c->hout.ensure(total));
+    unsigned char *h = c->hout.as<unsigned char>();
+    TRY(d2h(c, h + o_index, c->oindex.p, 4 * nN));
+    TRY(d2h(c, h + o_attr, c->oattr.p, nN));
+    TRY(d2h(c, h + o_dict, c->odict.p, 2 * fk * cs));
+    TRY(d2h(c, h + o_datten, c->odatten.p, fk));
+    TRY(sync(c));
+    collect_stage_times(c);
+    for (int i = 0; i < F; ++i) {
+        const GscFrame &f = c->h_frames[i];
+        gsc_frame_result &r = res[i];
+        r.N = f.N; r.R = newR[i]; r.divider = divider[i]; r.passes = passes[i]; r.err = err[i];
+        r.overfull = overfull[i]; r.reserved = 0;
+        if (r.index) memcpy(r.index, h + o_index + 4 * (size_t)f.chunk_off, 4 * (size_t)f.N);
+        if (r.attr) memcpy(r.attr, h + o_attr + (size_t)f.chunk_off, (size_t)f.N);
+        if (r.dict) memcpy(r.dict, h + o_dict + 2 * (size_t)i * Kmax * cs, 2 * (size_t)r.R * cs);
+        if (r.datten) memcpy(r.datten, h + o_datten + (size_t)i * Kmax, (size_t)r.R);
+    }
+    return GSC_OK;
+}
+
+extern "C" int gsc_encode_frames(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P,
+                                 gsc_frame_result *results) {
+    FpGuard g;
+    if (!c || !frames || n_frames <= 0 || !results) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames");
+    TRY(check_params(P));
+    CU(cudaSetDevice(c->device));
+    TRY(plan_batch(c, frames, n_frames, P->chunk_size, P->chunks_per_frame, P->precision, true, nullptr));
+    TRY(c->hpcm.ensure(2 * (size_t)c->pcm_samples));
+    for (int i = 0; i < n_frames; ++i) {
+        const GscFrame &f = c->h_frames[i];
+        for (int j = 0; j < f.C; ++j)
+            memcpy(c->hpcm.as<int16_t>() + f.pcm_off + (size_t)j * f.S, frames[i].pcm + (size_t)j * frames[i].stride,
+                   2 * (size_t)f.S);
+    }
+    TRY(c->pcm.ensure(2 * (size_t)c->pcm_samples));
+    TRY(h2d(c, c->pcm.p, c->hpcm.p, 2 * (size_t)c->pcm_samples));
+    TRY(upload_frames(c));
+    TRY(run_pipeline(c, P));
+    return gsc_fetch_results(c, n_frames, results);
+}
+
+// Device-resident variant: frames[i].pcm are device pointers into one buffer
+// that the caller owns; the library reads it in place.
+extern "C" int gsc_encode_frames_dev(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P) {
+    FpGuard g;
+    if (!c || !frames || n_frames <= 0) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames_dev");
+    TRY(check_params(P));
+    CU(cudaSetDevice(c->device));
+    const int16_t *base = frames[0].pcm;
+    for (int i = 1; i < n_frames; ++i) if (frames[i].pcm < base) base = frames[i].pcm;
+    TRY(plan_batch(c, frames, n_frames, P->chunk_size, P->chunks_per_frame, P->precision, false, base));
+    TRY(upload_frames(c));
+    // borrow the caller's buffer for the duration of the call
+    DevBuf saved = c->pcm;
+    c->pcm.p = const_cast<int16_t *>(base);
+    c->pcm.cap = ~(size_t)0;
+    int rc = run_pipeline(c, P);
+    c->pcm = saved;
+    return rc;
+}
+
+extern "C" int gsc_fp32_peak_probe(gsc_ctx *c, double *tflops) {
+    FpGuard g;
+    if (!c || !tflops) return set_err(GSC_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    TRY(c->misc.ensure(4 * (size_t)blocks * threads));
+    LAUNCH(c, k_ffma_probe, blocks, threads, 0, c->misc.as<float>(), 64);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(c->ev[0], c->stream));
+        LAUNCH(c, k_ffma_probe, blocks, threads, 0, c->misc.as<float>(), iters);
+        CU(cudaEventRecord(c->ev[8], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[8]));
+        double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    *tflops = best;
+    return GSC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// 1. legacy ABI (ext:112-123)
+// ---------------------------------------------------------------------------
+struct YakmoHandle {
+    unsigned k = 0;
+    int maxIter = 0, initType = 1;
+    unsigned rows = 0, cols = 0;
+    std::vector<float> X, cen;
+    bool trained = false;
+    gsc_ctx *ctx = nullptr;
+};
+
+extern "C" void *yakmo_create(uint32_t k, uint32_t restartCount, int32_t maxIter, int32_t initType, int32_t initSeed,
+                              int32_t doNormalize, int32_t isVerbose) {
+    FpGuard g;
+    (void)restartCount; (void)isVerbose;
+    if (doNormalize) { set_err(GSC_ERR_UNSUPPORTED, "yakmo_create: doNormalize is not supported"); return nullptr; }
+    if (initSeed) { set_err(GSC_ERR_UNSUPPORTED, "yakmo_create: only the fixed-seed mode (initSeed = 0) is supported"); return nullptr; }
+    if (k == 0 || k > GSC_MAX_K) { set_err(GSC_ERR_ARG, "yakmo_create: k out of range"); return nullptr; }
+    gsc_ctx *ctx = gsc_create(-1);
+    if (!ctx) return nullptr;
+    YakmoHandle *h = new (std::nothrow) YakmoHandle();
+    if (!h) { gsc_destroy(ctx); return nullptr; }
+    h->k = k; h->maxIter = maxIter < 0 ? 0 : maxIter; h->initType = initType; h->ctx = ctx;
+    return h;
+}
+extern "C" void yakmo_destroy(void *ay) {
+    if (!ay) return;
+    YakmoHandle *h = (YakmoHandle *)ay;
+    gsc_destroy(h->ctx);
+    delete h;
+}
+extern "C" void yakmo_load_train_data(void *ay, uint32_t rowCount, uint32_t colCount, float **dataset) {
+    if (!ay || !dataset) return;
+    FpGuard g;
+    YakmoHandle *h = (YakmoHandle *)ay;
+    h->rows = rowCount; h->cols = colCount;
+    h->X.resize((size_t)rowCount * colCount);
+    for (uint32_t i = 0; i < rowCount; ++i) memcpy(&h->X[(size_t)i * colCount], dataset[i], sizeof(float) * colCount);
+    h->trained = false;
+}
+extern "C" void yakmo_train_on_data(void *ay, int32_t *pointToCluster) {
+    if (!ay) return;
+    FpGuard g;
+    YakmoHandle *h = (YakmoHandle *)ay;
+    h->cen.assign((size_t)h->k * h->cols, 0.0f);
+    int rc = gsc_yakmo(h->ctx, h->X.data(), (int)h->rows, (int)h->cols, (int)h->k, h->initType, h->maxIter,
+                       h->cen.data(), pointToCluster, nullptr);
+    h->trained = (rc == GSC_OK);
+    if (rc != GSC_OK && pointToCluster)
+        for (uint32_t i = 0; i < h->rows; ++i) pointToCluster[i] = -1;
+}
+extern "C" void yakmo_get_centroids(void *ay, float **centroids) {
+    if (!ay || !centroids) return;
+    YakmoHandle *h = (YakmoHandle *)ay;
+    if (!h->trained) return;
+    for (unsigned i = 0; i < h->k; ++i) memcpy(centroids[i], &h->cen[(size_t)i * h->cols], sizeof(float) * h->cols);
+}
+
+struct AnnHandle {
+    gsc_ctx *ctx = nullptr;
+    int n = 0, dd = 0;
+    DevBuf pts, q, scratch, idx, err;
+};
+
+extern "C" void *ann_kdtree_create(float **pa, int32_t n, int32_t dd, int32_t bs, int32_t split) {
+    FpGuard g;
+    (void)bs; (void)split;
+    if (!pa || n <= 0 || dd <= 0) { set_err(GSC_ERR_ARG, "ann_kdtree_create: bad arguments"); return nullptr; }
+    gsc_ctx *ctx = gsc_create(-1);
+    if (!ctx) return nullptr;
+    AnnHandle *h = new (std::nothrow) AnnHandle();
+    if (!h) { gsc_destroy(ctx); return nullptr; }
+    h->ctx = ctx; h->n = n; h->dd = dd;
+    std::vector<float> flat((size_t)n * dd);
+    for (int i = 0; i < n; ++i) memcpy(&flat[(size_t)i * dd], pa[i], sizeof(float) * dd);
+    bool ok = h->pts.ensure(4 * (size_t)n * dd) == GSC_OK && h->q.ensure(4 * (size_t)dd) == GSC_OK &&
+              h->scratch.ensure(4 * (size_t)n) == GSC_OK && h->idx.ensure(4 * 1024) == GSC_OK &&
+              h->err.ensure(4 * 1024) == GSC_OK &&
+              cudaMemcpyAsync(h->pts.p, flat.data(), 4 * (size_t)n * dd, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+              cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (!ok) {
+        if (t_err.empty()) set_err(GSC_ERR_CUDA, "ann_kdtree_create: device upload failed");
+        h->pts.release(); h->q.release(); h->scratch.release(); h->idx.release(); h->err.release();
+        gsc_destroy(ctx); delete h;
+        return nullptr;
+    }
+    return h;
+}
+extern "C" void ann_kdtree_destroy(void *akd) {
+    if (!akd) return;
+    FpGuard g;
+    AnnHandle *h = (AnnHandle *)akd;
+    cudaSetDevice(h->ctx->device);
+    h->pts.release(); h->q.release(); h->scratch.release(); h->idx.release(); h->err.release();
+    gsc_destroy(h->ctx);
+    delete h;
+}
+static int ann_query(AnnHandle *h, const float *q, float eps, int cnt, int32_t *idxs, float *errs) {
+    if (!h || !q || cnt <= 0 || cnt > 1024) return set_err(GSC_ERR_ARG, "ann search: bad arguments");
+    if (eps != 0.0f) return set_err(GSC_ERR_UNSUPPORTED, "ann search: only eps = 0 (exact) is supported");
+    if (cnt > h->n) return set_err(GSC_ERR_ARG, "ann search: k > n");  // ANN: "Requesting more near neighbors than data points"
+    gsc_ctx *c = h->ctx;
+    CU(cudaSetDevice(c->device));
+    TRY(h2d(c, h->q.p, q, 4 * (size_t)h->dd));
+    LAUNCH(c, k_ann_query, 1, 256, 0, h->pts.as<float>(), h->n, h->dd, h->q.as<float>(), cnt, h->scratch.as<float>(),
+           h->idx.as<int>(), h->err.as<float>());
+    TRY(d2h(c, idxs, h->idx.p, 4 * (size_t)cnt));
+    TRY(d2h(c, errs, h->err.p, 4 * (size_t)cnt));
+    return sync(c);
+}
+extern "C" int32_t ann_kdtree_search(void *akd, float *q, float eps, float *err) {
+    FpGuard g;
+    int32_t idx = -1; float e = 0;
+    if (ann_query((AnnHandle *)akd, q, eps, 1, &idx, &e) != GSC_OK) return -1;
+    if (err) *err = e;
+    return idx;
+}
+extern "C" int32_t ann_kdtree_pri_search(void *akd, float *q, float eps, float *err) {
+    return ann_kdtree_search(akd, q, eps, err);
+}
+extern "C" void ann_kdtree_search_multi(void *akd, int32_t *idxs, float *errs, int32_t cnt, float *q, float eps) {
+    FpGuard g;
+    if (!idxs || !errs) return;
+    if (ann_query((AnnHandle *)akd, q, eps, cnt, idxs, errs) != GSC_OK)
+        for (int i = 0; i < cnt; ++i) { idxs[i] = -1; errs[i] = INFINITY; }
+}
+extern "C" void ann_kdtree_pri_search_multi(void *akd, int32_t *idxs, float *errs, int32_t cnt, float *q, float eps) {
+    ann_kdtree_search_multi(akd, idxs, errs, cnt, q, eps);
+}
