@@ -225,6 +225,9 @@ int gsc_fetch_results(gsc_ctx *ctx, int n_frames, gsc_frame_result *results);
  * centroid in the exact operation order instead of using its lower-bound
  * filter.  Results are identical by construction; the tests check that. */
 void gsc_debug_set_online_exact(int on);
+/* Debug hook: 1 = the seeding kernel evaluates yakmo's sequential float prefix
+ * sum with a one-warp serial chain instead of the exact parallel scan. */
+void gsc_debug_set_serial_scan(int on);
 
 /* FP32 FFMA throughput probe (roofline denominator for the k-means / search
  * kernels): returns measured TFLOP/s on the context's device. */

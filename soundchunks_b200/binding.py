@@ -26,7 +26,7 @@ EXPORTS = [
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
     "gsc_assign", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact",
+    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan",
 ]
 
 

@@ -342,6 +342,11 @@ static int stage_chunks(gsc_ctx *c, bool want_atten, bool want_dst, bool want_fe
         }                                     \
     } while (0)
 
+// Debug hook (tests): 1 = evaluate yakmo's float prefix sum with the one-warp serial chain
+// instead of the exact parallel scan; results must be identical.
+static int g_serial_scan = 0;
+extern "C" void gsc_debug_set_serial_scan(int on) { g_serial_scan = on ? 1 : 0; }
+
 template <int D>
 static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
     size_t smem = (size_t)((c->maxN + 31) / 32) * 4;
@@ -349,7 +354,8 @@ static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
     SMEM_OPTIN(k_seed<D>, smem);
     LAUNCH(c, k_seed<D>, c->F, GSC_SEED_THREADS, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), init_type,
            c->pnorm.as<float>(), c->up.as<float>(), c->r.as<float>(), c->sid.as<int>(),
-           want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax);
+           want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax,
+           g_serial_scan);
     return GSC_OK;
 }
 

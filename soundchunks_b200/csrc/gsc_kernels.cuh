@@ -207,6 +207,187 @@ __device__ __forceinline__ void gsc_load_row(const float *__restrict__ X, long l
 }
 
 #define GSC_SEED_THREADS 512
+#define GSC_SCAN_E 4                                   // elements per thread per attempt
+#define GSC_SCAN_WIN (GSC_SEED_THREADS * GSC_SCAN_E)   // elements per attempt
+
+// ---------------------------------------------------------------------------
+// Exact PARALLEL evaluation of the sequential float recurrence
+//     r[j] = fl(r[j-1] + a[j]),   r[-1] = +0          (yakmo: obj += up; r[j] = obj)
+// Float addition is not associative, so a tree reduction gives other bits.
+// But while the running sum stays inside one binade [2^E, 2^(E+1)) every
+// partial sum is an integer multiple S*u of u = ulp = 2^(E-23), and
+//     S_j = S_{j-1} + floor(a_j/u) + round_bit,
+// where round_bit depends only on the fraction of a_j/u and, for an exact tie,
+// on the PARITY of S (round half to even).  Each element is therefore a
+// function  parity -> increment, those functions compose associatively, and a
+// block-wide scan of them reproduces the sequential result bit for bit.
+// Elements that would leave the binade (or non-finite / huge ones) are found
+// by an index min-reduction, added with one real float addition, and the scan
+// restarts behind them in the new binade; a zero running sum is skipped in
+// parallel; short-progress stretches (the first few hundred elements, where
+// the sum doubles every few elements) fall back to a one-warp serial chain.
+// All threads of the CTA must call this; returns the final sum to everyone.
+// ---------------------------------------------------------------------------
+struct GscScanSmem {
+    int w0[GSC_SEED_THREADS / 32], w1[GSC_SEED_THREADS / 32];
+    int wv[GSC_SEED_THREADS / 32];
+    float run;
+    int pos;
+};
+
+__device__ __forceinline__ void gsc_scan_compose(int &f0, int &f1, int g0, int g1) {
+    // (f then g)(p) = f(p) + g((p + f(p)) & 1)
+    const int h0 = f0 + ((f0 & 1) ? g1 : g0);
+    const int h1 = f1 + (((1 + f1) & 1) ? g1 : g0);
+    f0 = h0; f1 = h1;
+}
+
+__device__ float gsc_seq_prefix(const float *__restrict__ a, float *__restrict__ r, int N, GscScanSmem &sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { sm.run = 0.0f; sm.pos = 0; }
+    __syncthreads();
+    for (;;) {
+        const int pos = sm.pos;
+        const float run = sm.run;
+        if (pos >= N) break;
+        const unsigned rb = __float_as_uint(run);
+        const int E0 = (int)((rb >> 23) & 0xffu);
+        const int wend = min(N, pos + GSC_SCAN_WIN);
+        const int j0 = pos + tid * GSC_SCAN_E;
+        int viol = N;  // first index this thread cannot certify
+
+        if (run == 0.0f) {
+            // 0 + a = a exactly: skip the zero run in parallel
+#pragma unroll
+            for (int e = 0; e < GSC_SCAN_E; ++e) {
+                const int j = j0 + e;
+                if (j < wend && viol == N) { if (a[j] != 0.0f) viol = j; }
+            }
+        } else if ((rb >> 31) == 0u && E0 >= 1 && E0 <= 254) {
+            // positive normal running sum: integer-domain scan within the binade
+            const int Sm = (int)((rb & 0x7fffffu) | 0x800000u);
+            int I[GSC_SCAN_E], cls[GSC_SCAN_E];
+#pragma unroll
+            for (int e = 0; e < GSC_SCAN_E; ++e) {
+                const int j = j0 + e;
+                I[e] = 0; cls[e] = 0;
+                if (j < wend) {
+                    const unsigned ab = __float_as_uint(a[j]);
+                    const int ef = (int)((ab >> 23) & 0xffu);
+                    int ma = (int)(ab & 0x7fffffu) | (ef ? 0x800000 : 0);
+                    const int ea = ef ? ef : 1;
+                    if (ab >> 31) ma = -ma;
+                    const int sh = ea - E0;
+                    if (ef == 255 || (sh > 1 && ma != 0)) { I[e] = 1 << 26; cls[e] = 3; }   // non-finite / huge
+                    else if (sh >= 0) { I[e] = ma << sh; }
+                    else {
+                        const int k = -sh;
+                        if (k > 26) { if (ma < 0) { I[e] = -1; cls[e] = 1; } }
+                        else {
+                            I[e] = ma >> k;                        // floor
+                            const int rem = ma & ((1 << k) - 1);   // fraction * 2^k, in [0, 2^k)
+                            const int half = 1 << (k - 1);
+                            cls[e] = rem < half ? 0 : (rem > half ? 1 : 2);
+                        }
+                    }
+                }
+            }
+            // this thread's elements as a function parity -> increment
+            int f0 = 0, f1 = 1;   // running S (mod offset) for start parity 0 / 1
+#pragma unroll
+            for (int e = 0; e < GSC_SCAN_E; ++e) {
+                const int t0 = f0 + I[e], t1 = f1 + I[e];
+                f0 = t0 + ((cls[e] == 1) | ((cls[e] == 2) & (t0 & 1)));
+                f1 = t1 + ((cls[e] == 1) | ((cls[e] == 2) & (t1 & 1)));
+            }
+            f1 -= 1;
+            // inclusive warp scan
+            int s0 = f0, s1 = f1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int p0 = __shfl_up_sync(0xffffffffu, s0, o), p1 = __shfl_up_sync(0xffffffffu, s1, o);
+                if (lane >= o) { int q0 = p0, q1 = p1; gsc_scan_compose(q0, q1, s0, s1); s0 = q0; s1 = q1; }
+            }
+            if (lane == 31) { sm.w0[warp] = s0; sm.w1[warp] = s1; }
+            __syncthreads();
+            int x0 = 0, x1 = 0;
+            for (int w = 0; w < warp; ++w) gsc_scan_compose(x0, x1, sm.w0[w], sm.w1[w]);
+            {
+                int e0 = __shfl_up_sync(0xffffffffu, s0, 1), e1 = __shfl_up_sync(0xffffffffu, s1, 1);
+                if (lane == 0) { e0 = 0; e1 = 0; }
+                gsc_scan_compose(x0, x1, e0, e1);
+            }
+            int S = Sm + ((Sm & 1) ? x1 : x0);
+            // replay own elements with the true S, certify and emit
+#pragma unroll
+            for (int e = 0; e < GSC_SCAN_E; ++e) {
+                const int j = j0 + e;
+                if (j < wend && viol == N) {
+                    const int t = S + I[e];
+                    const int Sn = t + ((cls[e] == 1) | ((cls[e] == 2) & (t & 1)));
+                    if (cls[e] == 3 || t < (1 << 23) || Sn >= (1 << 24) || S < (1 << 23) || S >= (1 << 24)) viol = j;
+                    else { S = Sn; r[j] = __uint_as_float(((unsigned)E0 << 23) | ((unsigned)Sn & 0x7fffffu)); }
+                }
+            }
+        } else {
+            viol = pos;  // negative / denormal / non-finite running sum: one real addition
+        }
+        // first uncertified index of the window
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) viol = min(viol, __shfl_xor_sync(0xffffffffu, viol, o));
+        if (lane == 0) sm.wv[warp] = viol;
+        __syncthreads();
+        int v = N;
+#pragma unroll
+        for (int w = 0; w < GSC_SEED_THREADS / 32; ++w) v = min(v, sm.wv[w]);
+        if (v > wend) v = wend;
+        if (run == 0.0f) {
+            // zeros up to v (exclusive); element v (if any) becomes the sum
+#pragma unroll
+            for (int e = 0; e < GSC_SCAN_E; ++e) { const int j = j0 + e; if (j < v) r[j] = 0.0f; }
+            __syncthreads();
+            if (tid == 0) {
+                if (v < wend) { const float nv = 0.0f + a[v]; r[v] = nv; sm.run = nv; sm.pos = v + 1; }
+                else sm.pos = wend;
+            }
+        } else if (v - pos < 64 && v < wend) {
+            // little progress: one-warp serial chain over the next 256 elements
+            __syncthreads();
+            if (warp == 0) {
+                float rr = run;
+                const int lim = min(N, pos + 256);
+                for (int b0 = pos; b0 < lim; b0 += 32) {
+                    const int j = b0 + lane;
+                    const float val = (j < lim) ? a[j] : 0.0f;
+                    float mine = 0.0f;
+                    const int cntl = min(32, lim - b0);
+                    for (int l = 0; l < cntl; ++l) {
+                        const float vv = __shfl_sync(0xffffffffu, val, l);
+                        rr = rr + vv;
+                        if (lane == l) mine = rr;
+                    }
+                    if (j < lim) r[j] = mine;
+                }
+                if (lane == 0) { sm.run = rr; sm.pos = lim; }
+            }
+        } else {
+            __syncthreads();   // r[v-1] visible
+            if (tid == 0) {
+                if (v < wend) {
+                    const float before = (v == pos) ? run : r[v - 1];
+                    const float nv = before + a[v];
+                    r[v] = nv; sm.run = nv; sm.pos = v + 1;
+                } else {
+                    sm.run = r[wend - 1]; sm.pos = wend;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const float total = sm.run;
+    __syncthreads();
+    return total;
+}
 
 template <int D>
 __global__ void __launch_bounds__(GSC_SEED_THREADS) k_seed(const GscFrame *__restrict__ frames,
@@ -219,11 +400,12 @@ __global__ void __launch_bounds__(GSC_SEED_THREADS) k_seed(const GscFrame *__res
                                                            int *__restrict__ seeds,       // [F][Kmax] or null
                                                            float *__restrict__ cen,       // [F][Kmax][D] seeds out
                                                            float *__restrict__ cnorm,     // [F][Kmax]
-                                                           int Kmax) {
+                                                           int Kmax, int serial_scan) {
     extern __shared__ unsigned chosen[];  // N bits
     __shared__ float s_c[D];
     __shared__ float s_cn;
     __shared__ float s_obj;
+    __shared__ GscScanSmem s_scan;
     const GscFrame f = frames[blockIdx.x];
     const int K = f.K, N = f.N;
     if (K <= 0) return;
@@ -286,22 +468,27 @@ __global__ void __launch_bounds__(GSC_SEED_THREADS) k_seed(const GscFrame *__res
             if (i == 0 || upf[j] > d) { upf[j] = d; sidf[j] = i; }
         }
         __syncthreads();
-        if (i < K - 1 && init_type == 1 && tid < 32) {
-            // obj := 0; for j: obj += up[j]; r[j] := obj   (sequential float chain)
-            float run = 0.0f;
-            for (int base = 0; base < N; base += 32) {
-                const int j = base + tid;
-                const float v = (j < N) ? upf[j] : 0.0f;
-                float mine = 0.0f;
-                const int lim = min(32, N - base);
-                for (int l = 0; l < lim; ++l) {
-                    float vv = __shfl_sync(0xffffffffu, v, l);
-                    run = run + vv;
-                    if (tid == l) mine = run;
+        if (i < K - 1 && init_type == 1) {
+            // obj := 0; for j: obj += up[j]; r[j] := obj   (the reference's sequential float chain)
+            if (!serial_scan) {
+                const float tot = gsc_seq_prefix(upf, rf, N, s_scan);
+                if (tid == 0) s_obj = tot;
+            } else if (tid < 32) {
+                float run = 0.0f;
+                for (int base = 0; base < N; base += 32) {
+                    const int j = base + tid;
+                    const float v = (j < N) ? upf[j] : 0.0f;
+                    float mine = 0.0f;
+                    const int lim = min(32, N - base);
+                    for (int l = 0; l < lim; ++l) {
+                        float vv = __shfl_sync(0xffffffffu, v, l);
+                        run = run + vv;
+                        if (tid == l) mine = run;
+                    }
+                    if (j < N) rf[j] = mine;
                 }
-                if (j < N) rf[j] = mine;
+                if (tid == 0) s_obj = run;
             }
-            if (tid == 0) s_obj = run;
         }
         __syncthreads();
     }

@@ -83,6 +83,26 @@ def test_yakmo_seeding(ctx, oracle, K, seconds):
     assert np.array_equal(l_gpu, l_ref), "reassignment labels"
 
 
+def test_yakmo_seeding_full_size_and_scan_modes(ctx, oracle):
+    """Full-size frame (N ~ 96k, K = 4096): the exact parallel evaluation of yakmo's sequential float
+    prefix sum must give the oracle's seed sequence, and so must the one-warp serial chain."""
+    import soundchunks_b200.binding as b
+    pcm = _quiet(_audio(4.0, 48000, 2, 77))
+    raw, attr, atten, feat, dst = oracle.make_chunks(pcm, 4, 12, 6)
+    c_ref, l_ref, s_ref = oracle.yakmo(feat, 4096)
+    c_gpu, l_gpu, s_gpu = ctx.yakmo(feat, 4096)
+    assert np.array_equal(s_gpu, s_ref), f"first divergence at seed {int(np.argmax(s_gpu != s_ref))}"
+    assert _same_f32(c_gpu, c_ref)
+    lib = b.load_library()
+    lib.gsc_debug_set_serial_scan(1)
+    try:
+        c2, l2, s2 = ctx.yakmo(feat[:20000], 300)
+    finally:
+        lib.gsc_debug_set_serial_scan(0)
+    c3, l3, s3 = ctx.yakmo(feat[:20000], 300)
+    assert np.array_equal(s2, s3) and _same_f32(c2, c3) and np.array_equal(l2, l3)
+
+
 def test_yakmo_random_init_and_iters(ctx, oracle):
     pcm, raw, attr, feat = _features(oracle, 0.1)
     c_ref, l_ref, s_ref = oracle.yakmo(feat, 32, init_type=0, max_iter=0)
