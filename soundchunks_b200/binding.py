@@ -26,7 +26,7 @@ EXPORTS = [
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
     "gsc_assign", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan",
+    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters",
 ]
 
 
@@ -186,6 +186,11 @@ class Context:
 
     def reset_stats(self):
         self._ck(self.L.gsc_reset_stats(self.h))
+
+    def online_counters(self, n_frames: int) -> np.ndarray:
+        out = np.zeros((n_frames, 8), np.uint64)
+        self._ck(self.L.gsc_debug_online_counters(C.c_void_p(self.h), _vp(out), n_frames))
+        return out
 
     def fp32_peak_tflops(self) -> float:
         v = C.c_double(0)

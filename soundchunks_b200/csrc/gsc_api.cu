@@ -118,7 +118,7 @@ struct gsc_ctx {
     // device buffers
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
-        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc;
+        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg;
     HostBuf hpcm, hout;
     bool attr_set[4] = {false, false, false, false};
 };
@@ -181,7 +181,7 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
-                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc};
+                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg};
     for (DevBuf *b : bufs) b->release();
     c->hpcm.release();
     c->hout.release();
@@ -397,13 +397,14 @@ static int stage_lloyd_update(gsc_ctx *c, int D) {
     return GSC_OK;
 }
 
-template <int D, int CPT>
+template <int D, int CPT, int T>
 static int online_launch(gsc_ctx *c, double tol, int max_passes, int force_exact) {
-    size_t smem = sizeof(GscOnlineSmem<D>) + sizeof(int) * 2 * GSC_ON_T * CPT;
-    auto k_online_inst = k_online<D, CPT>;
+    size_t smem = GscOnLayout<D, CPT, T>::TOTAL;
+    auto k_online_inst = k_online<D, CPT, T>;
     SMEM_OPTIN(k_online_inst, smem);
-    LAUNCH(c, k_online_inst, c->F, GSC_ON_T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
-           c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, force_exact);
+    LAUNCH(c, k_online_inst, c->F, T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
+           c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, force_exact,
+           c->dbg.as<unsigned long long>());
     return GSC_OK;
 }
 
@@ -417,6 +418,15 @@ static int g_force_exact = -1;
 // Debug hook (tests): 1 = score every centroid exactly in the online kernel
 // instead of using the lower-bound filter; results must be identical.
 extern "C" void gsc_debug_set_online_exact(int on) { g_force_exact = on ? 1 : 0; }
+// Debug: counters of the last online k-means launch, 8 x uint64 per frame:
+// batches, points, exhaustive points, cuts (verification), cuts (list overflow), candidates.
+extern "C" int gsc_debug_online_counters(gsc_ctx *c, unsigned long long *out, int n_frames) {
+    if (!c || !out || n_frames > c->F || !c->dbg.p) return set_err(GSC_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out, c->dbg.p, 64 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return GSC_OK;
+}
 static int force_exact_flag() {
     if (g_force_exact < 0) {
         const char *e = getenv("GSC_ONLINE_EXACT");
@@ -428,20 +438,25 @@ static int force_exact_flag() {
 // online k-means; labels buffer must already hold per-point guesses
 static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     TRY(c->passes.ensure(4 * (size_t)c->F)); TRY(c->err.ensure(8 * (size_t)c->F));
+    TRY(c->dbg.ensure(64 * (size_t)c->F));
     CU(cudaMemsetAsync(c->passes.p, 0, 4 * (size_t)c->F, c->stream));
     CU(cudaMemsetAsync(c->err.p, 0, 8 * (size_t)c->F, c->stream));
+    CU(cudaMemsetAsync(c->dbg.p, 0, 64 * (size_t)c->F, c->stream));
     const double tol = int_power10_neg(precision);
     const int K = c->Kmax, fe = force_exact_flag();
+    // CTA shape by dictionary size: small K -> small CTAs so that several frames share an SM
     if (D == 8) {
-        if (K <= 512) return online_launch<8, 1>(c, tol, max_passes, fe);
-        if (K <= 1024) return online_launch<8, 2>(c, tol, max_passes, fe);
-        if (K <= 2048) return online_launch<8, 4>(c, tol, max_passes, fe);
-        if (K <= 4096) return online_launch<8, 8>(c, tol, max_passes, fe);
+        if (K <= 256) return online_launch<8, 4, 64>(c, tol, max_passes, fe);
+        if (K <= 512) return online_launch<8, 8, 64>(c, tol, max_passes, fe);
+        if (K <= 1024) return online_launch<8, 8, 128>(c, tol, max_passes, fe);
+        if (K <= 2048) return online_launch<8, 16, 128>(c, tol, max_passes, fe);
+        if (K <= 4096) return online_launch<8, 16, 256>(c, tol, max_passes, fe);
     } else if (D == 4) {
-        if (K <= 512) return online_launch<4, 1>(c, tol, max_passes, fe);
-        if (K <= 1024) return online_launch<4, 2>(c, tol, max_passes, fe);
-        if (K <= 2048) return online_launch<4, 4>(c, tol, max_passes, fe);
-        if (K <= 4096) return online_launch<4, 8>(c, tol, max_passes, fe);
+        if (K <= 256) return online_launch<4, 4, 64>(c, tol, max_passes, fe);
+        if (K <= 512) return online_launch<4, 8, 64>(c, tol, max_passes, fe);
+        if (K <= 1024) return online_launch<4, 8, 128>(c, tol, max_passes, fe);
+        if (K <= 2048) return online_launch<4, 16, 128>(c, tol, max_passes, fe);
+        if (K <= 4096) return online_launch<4, 16, 256>(c, tol, max_passes, fe);
     }
     return set_err(GSC_ERR_UNSUPPORTED, "online k-means supports D in {4, 8} and K <= 4096 (got D=%d K=%d)", D, K);
 }
