@@ -229,8 +229,8 @@ void gsc_debug_set_online_exact(int on);
  * sum with a one-warp serial chain instead of the exact parallel scan. */
 void gsc_debug_set_serial_scan(int on);
 /* Debug: counters of the last online k-means launch, 8 x uint64 per frame:
- * batches, points, exhaustive points, cuts by verification, cuts by list
- * overflow, candidates scored exactly. */
+ * batches, points, exhaustive points, resolver rounds, full candidate lists,
+ * candidates scored exactly, phase-1 cycles, phase-2 cycles. */
 int gsc_debug_online_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
 
 /* FP32 FFMA throughput probe (roofline denominator for the k-means / search

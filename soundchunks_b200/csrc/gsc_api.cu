@@ -397,6 +397,18 @@ static int stage_lloyd_update(gsc_ctx *c, int D) {
     return GSC_OK;
 }
 
+// Slack on the candidate threshold of the online kernel (a tuning knob: any value gives the same
+// results, see gsc_online.cuh phase 2).  GSC_ONLINE_SLACK overrides the default.
+static float online_slack() {
+    static float v = -1.0f;
+    if (v < 0.0f) {
+        const char *e = getenv("GSC_ONLINE_SLACK");
+        float x = e ? (float)atof(e) : 1.0f;
+        v = (x >= 1.0f && x <= 16.0f) ? x : 1.0f;
+    }
+    return v;
+}
+
 template <int D, int CPT, int T>
 static int online_launch(gsc_ctx *c, double tol, int max_passes, int force_exact) {
     size_t smem = GscOnLayout<D, CPT, T>::TOTAL;
@@ -404,7 +416,7 @@ static int online_launch(gsc_ctx *c, double tol, int max_passes, int force_exact
     SMEM_OPTIN(k_online_inst, smem);
     LAUNCH(c, k_online_inst, c->F, T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
            c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, force_exact,
-           c->dbg.as<unsigned long long>());
+           online_slack(), c->dbg.as<unsigned long long>());
     return GSC_OK;
 }
 

@@ -2,8 +2,9 @@
 // TFrame.KNNScanReduce), one point at a time against the LIVE centroids.
 //
 // The rule is sequential in the points (each update moves one centroid before
-// the next query), so the parallelism is (a) across the K centroids inside a
-// frame and (b) across the frames of a batch: ONE CTA PER FRAME.
+// the next query).  The kernel reproduces that sequence bit for bit while
+// working on 32 points at a time: ONE CTA PER FRAME, the frames of a batch run
+// side by side on the SMs.
 //
 // Per point (arithmetic of the result is the reference's, bit for bit):
 //   best  := argmin_c  d(x, c),  d = sum_k (x_k - c_k)^2   float, left to
@@ -15,47 +16,58 @@
 // Data placement (K = 4096, D = 8):
 //   shared memory  exact centroid rows K x 8 fp32 = 128 KB (the truth; read
 //                  only for exact scoring and updates), per-centroid rate
-//                  16 KB, counts 2 x 16 KB, point tile, candidate lists
+//                  16 KB, counts 2 x 16 KB, moved flags 4 KB, point tile 8 KB,
+//                  candidate lists 8 KB
 //   registers      FILTER copy: first DF = 4 dims of the thread's CPT = 16
 //                  centroids (64 regs) + h_c = -0.5|c|^2(1-g) (16 regs)
 //   HBM            one 32-byte row per point per pass (streamed through smem)
 //
-// Schedule: points are taken in batches of up to B = 8.
-//  Phase 1 (all warps, codebook frozen).  For every point b of the batch each
-//    thread evaluates, over the first DF dimensions of its centroids,
+// Schedule: points are taken in batches of B = 32 (lane b of warp 0 = point b).
+//  Phase 1 (all warps, codebook frozen at the batch start S0).  For every point
+//    each thread evaluates, over the first DF dimensions of its centroids,
 //        s_c = x.c + h_c                          (DF FFMAs per centroid)
 //    which certifies the LOWER bound
 //        lb_c = |x|^2(1-g) - 2 s_c <= sum_{k<DF}(x_k-c_k)^2 <= d(x,c)
 //    (dropped squared terms are >= 0 and tiny -- the 1e-5-scaled cepstral
 //    features, enc:362; g = 2^-17 covers every rounding of both forms).
-//    Centroids with lb_c <= U_b are scored in the exact operation order and
-//    their (d bits << 32 | index) keys appended to the point's list.  U_b is
-//    the exact distance to the centroid the point chose in the previous pass
-//    (its seed cell in pass 0).
-//  Phase 2 (one warp, lane b = point b, strictly in point order).  The winner
-//    of point t is the minimum key over (a) its list minus entries of
-//    centroids moved by points 0..t-1 of this batch and (b) fresh exact
-//    distances to those moved centroids; it is ACCEPTED iff d_win <= U_t --
-//    then every unmoved centroid with d <= d_win had lb <= U_t and was scored,
-//    and every moved one is scored fresh, so the key minimum is the exact
-//    argmin with the lowest index on ties.  If the test fails (or a list
-//    overflowed) the batch is cut before point t, which then leads the next
-//    batch with a fresh bound (always sufficient); a cut at t = 0 switches to
-//    an exhaustive scoring of that one point.  After each accepted point the
-//    row, counts, label and error term are updated and the later lanes score
-//    their points against the new row.
-// Two block barriers per batch.  Shared memory is addressed through an opaque
-// 32-bit base (inline ld/st.shared) so the shared-window base is not
-// rematerialised (S2UR SR_CgaCtaId) inside the loops.
+//    Centroids with lb_c <= U_b are appended to the point's candidate list.
+//    U_b is the exact distance to the centroid the point chose in the previous
+//    pass (its seed cell in pass 0).
+//  Phase 1.5 (all warps): warp <-> point, lane <-> list slot.  Every candidate
+//    is scored in the exact operation order, its (d bits << 32 | index) key
+//    replaces the slot and a warp reduction leaves the point's best key.
+//  Phase 2 (warp 0) resolves the batch in ROUNDS.  In a round every unresolved
+//    lane t proposes the minimum of (a) its best list key among centroids not
+//    moved since S0 and (b) its best fresh key among centroids moved in this
+//    batch.  The proposal is CERTIFIED iff d_win <= U_t and the list did not
+//    overflow: every unmoved centroid with d <= d_win has lb <= U_t and is on
+//    the list, every moved one was scored fresh, so the key minimum is the
+//    exact argmin with the lowest index on ties.  All proposing lanes compute
+//    their updated rows speculatively; lane t then scores the rows of lanes
+//    u < t and is in CONFLICT if one of them is its own winner or beats it.
+//    Lanes before the first conflicting / uncertified lane are exactly what
+//    the sequential rule produces (by induction: nothing before them touches
+//    their winner or offers a closer row) and commit together; the rest go to
+//    the next round with the fresh keys they just computed.  The pair scoring
+//    of a round is spread over all warps (warp w takes the rows u = t0+w,
+//    t0+w+W, ...), warp 0 proposes and commits.  An uncertified lane at the
+//    head of a round is resolved by RE-FILTERING that one point with the whole
+//    CTA against its best known exact distance (always a valid bound; -inf
+//    threshold = exhaustive scan when nothing is known), inside the same batch.
+// Shared memory is addressed through an opaque 32-bit base (inline ld/st.shared)
+// so the shared-window base is not rematerialised (S2UR SR_CgaCtaId) in loops.
 #pragma once
 #include "gsc_device.cuh"
 
 #define GSC_ON_TP 256         // points per shared-memory tile
-#define GSC_ON_B 8            // points per batch
-#define GSC_ON_L 16           // candidate list capacity per point
+#define GSC_ON_B 32           // points per batch (one per lane of the resolving warp)
+#define GSC_ON_L 32           // candidate list capacity per point (one slot per lane)
 #define GSC_ON_G 7.62939453125e-06f   // 2^-17
 #define GSC_NONE 0xffffffffu
 #define GSC_KNONE 0xffffffffffffffffull
+#define GSC_MODE_DONE 0
+#define GSC_MODE_REFILTER 1
+#define GSC_MODE_SCAN 2
 
 // ---- shared-memory access through an opaque 32-bit address -------------------
 __device__ __forceinline__ unsigned gsc_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -76,7 +88,11 @@ __device__ __forceinline__ void gsc_sts_d(unsigned a, double v) { asm volatile("
 __device__ __forceinline__ void gsc_sts_f4(unsigned a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void gsc_atoms_or(unsigned a, unsigned v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ int gsc_atoms_add(unsigned a, int v) { int o; asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
+
+__device__ __forceinline__ int gsc_lds_u8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return (int)v; }
+__device__ __forceinline__ void gsc_sts_u8(unsigned a, int v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 template <int D>
 __device__ __forceinline__ void gsc_lds_row(unsigned a, float (&r)[D]) {
@@ -111,6 +127,14 @@ __device__ __forceinline__ float gsc_rate(int cnt) {  // enc:735
     return (float)(1.0 / sqrt((double)cnt));
 }
 
+// minimum of 64-bit keys over a warp (two 32-bit redux steps)
+__device__ __forceinline__ unsigned long long gsc_warp_min_key(unsigned long long k) {
+    const unsigned kd = gsc_kd(k), ki = gsc_ki(k);
+    const unsigned m = __reduce_min_sync(0xffffffffu, kd);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, kd == m ? ki : GSC_NONE);
+    return gsc_pack(m, mi);
+}
+
 // shared-memory layout (byte offsets from the base)
 template <int D, int CPT, int T>
 struct GscOnLayout {
@@ -118,20 +142,31 @@ struct GscOnLayout {
     static constexpr unsigned X = 0;                                  // float [TP][D]
     static constexpr unsigned HX = X + GSC_ON_TP * D * 4;             // float [TP]
     static constexpr unsigned G = HX + GSC_ON_TP * 4;                 // int   [TP]
-    static constexpr unsigned ET = G + GSC_ON_TP * 4;                 // float [TP]
-    static constexpr unsigned LIST = ET + GSC_ON_TP * 4;              // u64   [B][L]
+    static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [B][L]
     static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B]
-    static constexpr unsigned MOVED = LISTN + GSC_ON_B * 4;           // int   [B]
-    static constexpr unsigned WKEY = MOVED + GSC_ON_B * 4;            // u64   [32]
-    static constexpr unsigned NMOVED = WKEY + 32 * 8;                 // int
-    static constexpr unsigned POSN = NMOVED + 4;                      // int
-    static constexpr unsigned EXH = POSN + 4;                         // int
-    static constexpr unsigned STOP = EXH + 4;                         // int
-    static constexpr unsigned ERR = STOP + 4;                         // double (8-aligned)
-    static constexpr unsigned RATE = ((ERR + 8 + 15) / 16) * 16;      // float [KP]
+    static constexpr unsigned ABEST = LISTN + GSC_ON_B * 4;           // u64   [B]
+    static constexpr unsigned MOVED = ABEST + GSC_ON_B * 8;           // int   [B]
+    static constexpr unsigned ROWS = MOVED + GSC_ON_B * 4;            // float [B][D]
+    static constexpr unsigned WS = ROWS + GSC_ON_B * D * 4;           // int   [B]
+    static constexpr unsigned ETB = WS + GSC_ON_B * 4;                // float [2][B]
+    static constexpr unsigned WKEY = ETB + 2 * GSC_ON_B * 4;          // u64   [32]
+    static constexpr unsigned FK = WKEY + 32 * 8;                     // u64   [B(u)][B(lane)] fresh keys of a round
+    static constexpr unsigned KEYS = FK + GSC_ON_B * GSC_ON_B * 8;    // u64   [B] proposals of a round
+    static constexpr unsigned CB = KEYS + GSC_ON_B * 8;               // u32   [B] conflict ballots per row u
+    static constexpr unsigned DIRTY = CB + GSC_ON_B * 4;              // u32   [T] moved centroids per owner thread
+    static constexpr unsigned T0 = DIRTY + T * 4;                     // int
+    static constexpr unsigned TMAX = T0 + 4;                          // int
+    static constexpr unsigned MODE = TMAX + 4;                        // int
+    static constexpr unsigned EPOINT = MODE + 4;                      // int
+    static constexpr unsigned ETHR = EPOINT + 4;                      // float
+    static constexpr unsigned STOP = ETHR + 4;                        // int
+    static constexpr unsigned ERR = ((STOP + 4 + 7) / 8) * 8;         // double
+    static constexpr unsigned MFLAG = ((ERR + 8 + 15) / 16) * 16;     // u8    [KP]
+    static constexpr unsigned RATE = ((MFLAG + KP + 15) / 16) * 16;   // float [KP]
     static constexpr unsigned CNT = RATE + KP * 4;                    // int   [2][KP]
     static constexpr unsigned C = ((CNT + 2 * KP * 4 + 15) / 16) * 16;  // float [KP][D]
     static constexpr unsigned TOTAL = C + KP * D * 4;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget of one SM");
 };
 
 template <int D, int CPT, int T>
@@ -141,13 +176,15 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                               int *__restrict__ labels,          // [sumN] in: guesses, out: labels
                                               int *__restrict__ passes_out,      // [F]
                                               double *__restrict__ err_out,      // [F]
-                                              double tol, int max_passes, int Kmax, int force_exact,
+                                              double tol, int max_passes, int Kmax, int force_exact, float slack,
                                               unsigned long long *__restrict__ dbg) {
     using Ly = GscOnLayout<D, CPT, T>;
+    static_assert(T >= 64, "thread 32 accumulates the error sum");
     constexpr int DF = (D >= 8) ? D / 2 : D;   // filter dimensions
     constexpr int W = T / 32;
     constexpr int KP = T * CPT;
     constexpr int B = GSC_ON_B, L = GSC_ON_L;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smraw[];
     const unsigned sb = gsc_opaque(gsc_smem_u32(smraw));
 
@@ -176,14 +213,17 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         h[j] = -0.5f * nc * (1.0f - GSC_ON_G);
     }
     for (int j = tid; j < 2 * KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
-    if (tid < B) { gsc_sts_i(sb + Ly::LISTN + 4u * tid, 0); gsc_sts_i(sb + Ly::MOVED + 4u * tid, 0); }
+    for (int j = tid; j < KP / 4; j += T) gsc_sts_i(sb + Ly::MFLAG + 4u * j, 0);
+    gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
+    if (tid < B) gsc_sts_i(sb + Ly::LISTN + 4u * tid, 0);
     if (tid == 0) {
         gsc_sts_d(sb + Ly::ERR, 3.40282346638528860e+38);
-        gsc_sts_i(sb + Ly::STOP, 0); gsc_sts_i(sb + Ly::NMOVED, 0); gsc_sts_i(sb + Ly::EXH, 0); gsc_sts_i(sb + Ly::POSN, 0);
+        gsc_sts_i(sb + Ly::STOP, 0); gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
     }
     __syncthreads();
 
-    unsigned long long c_ph1 = 0, c_ph2 = 0, c_t0 = 0; unsigned long long c_batches = 0, c_exh = 0, c_cut_verify = 0, c_cut_over = 0, c_points = 0, c_cands = 0;
+    unsigned long long c_ph1 = 0, c_ph2 = 0, c_t0 = 0;
+    unsigned long long c_batches = 0, c_exh = 0, c_rounds = 0, c_over = 0, c_points = 0, c_cands = 0;
     int iter = 0;
     for (;;) {
         const int odd = iter & 1;
@@ -193,7 +233,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         // rate of every centroid for this pass (cnt_prev is constant during a pass), enc:735
         for (int j = tid; j < KP; j += T) gsc_sts_f(sb + Ly::RATE + 4u * j, gsc_rate(gsc_lds_i(cnt_prev + 4u * j)));
         __syncthreads();
-        if (tid == 0) gsc_sts_d(sb + Ly::ERR, 0.0);
+        double e_run = 0.0;   // thread 32: enc:743 Double sum in point order, one batch behind the resolver
+        int nbatch = 0, prev_nb = 0;
 
         for (int base = 0; base < N; base += GSC_ON_TP) {
             const int tn = min(GSC_ON_TP, N - base);
@@ -212,248 +253,306 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
             }
             __syncthreads();  // (C)
 
-            int pos = 0;
-            while (pos < tn) {
+            for (int pos = 0; pos < tn; pos += B) {
                 const int nb = min(B, tn - pos);
-                const int exh = force_exact ? 1 : gsc_lds_i(sb + Ly::EXH);
                 if (tid == 0) c_t0 = clock64();
+                // ============ phase 0: refresh the filter copy of this thread's moved centroids ============
+                {
+                    const unsigned dirty = (unsigned)gsc_lds_i(sb + Ly::DIRTY + 4u * tid);
+                    if (dirty) {
+                        gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j)
+                            if (dirty & (1u << j)) {
+                                float r[D];
+                                gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
+                                float nc = 0.0f;
+#pragma unroll
+                                for (int k = 0; k < DF; ++k) { fc[j][k] = r[k]; nc = fmaf(r[k], r[k], nc); }
+                                h[j] = -0.5f * nc * (1.0f - GSC_ON_G);
+                            }
+                    }
+                }
                 // ============ phase 1: all warps, codebook frozen ============
-                {   // refresh the filter copy of centroids moved by the previous batch
-                    const int nm = gsc_lds_i(sb + Ly::NMOVED);
-                    for (int m = 0; m < nm; ++m) {
-                        const int id = gsc_lds_i(sb + Ly::MOVED + 4u * m);
-                        if (id >= first && id < first + CPT) {
-                            float r[D];
-                            gsc_lds_row<D>(sb + Ly::C + (unsigned)id * D * 4, r);
-                            float nc = 0.0f;
+                float xb[D];              // lane b of every warp: point pos+b
+                float Umine = INFINITY;   // ... and its bound
 #pragma unroll
-                            for (int k = 0; k < DF; ++k) nc = fmaf(r[k], r[k], nc);
-                            const float hn = -0.5f * nc * (1.0f - GSC_ON_G);
-                            const unsigned um = 1u << (id - first);   // bit mask, not `id - first == j` (see gsc_device.cuh)
+                for (int k = 0; k < D; ++k) xb[k] = 0.0f;
+                if (lane < nb) {
+                    const int p = pos + lane;
+                    const int g = gsc_lds_i(sb + Ly::G + 4u * p);
+                    float r[D];
+                    gsc_lds_row<D>(sb + Ly::X + (unsigned)p * D * 4, xb);
+                    gsc_lds_row<D>(sb + Ly::C + (unsigned)g * D * 4, r);
+                    const float d = gsc_ann_dist<D>(xb, r);
+                    Umine = (d == d) ? d * slack : INFINITY;   // any number is a valid threshold; see phase 2
+                }
+                if (!force_exact) {
+#pragma unroll 2
+                    for (int b = 0; b < nb; ++b) {
+                        const int p = pos + b;
+                        const float U = __shfl_sync(FULL, Umine, b);
+                        const float thr = gsc_lds_f(sb + Ly::HX + 4u * p) - 0.5f * U;   // candidate iff s >= thr (lb <= U)
+                        float xq[DF];
+                        if (DF == 4) {
+                            const float4 t4 = gsc_lds_f4(sb + Ly::X + (unsigned)p * D * 4);
+                            xq[0] = t4.x; xq[1] = t4.y; xq[2] = t4.z; xq[3] = t4.w;
+                        } else {
 #pragma unroll
-                            for (int j = 0; j < CPT; ++j)
-                                if (um & (1u << j)) {
+                            for (int k = 0; k < DF; ++k) xq[k] = gsc_lds_f(sb + Ly::X + (unsigned)(p * D + k) * 4u);
+                        }
+                        float s[CPT];
 #pragma unroll
-                                    for (int k = 0; k < DF; ++k) fc[j][k] = r[k];
-                                    h[j] = hn;
-                                }
+                        for (int j = 0; j < CPT; ++j) s[j] = h[j];
+#pragma unroll
+                        for (int k = 0; k < DF; ++k)
+#pragma unroll
+                            for (int j = 0; j < CPT; ++j) s[j] = fmaf(xq[k], fc[j][k], s[j]);
+                        float smax = s[0];
+#pragma unroll
+                        for (int j = 1; j < CPT; ++j) smax = fmaxf(smax, s[j]);   // NaN-safe: fmaxf ignores NaN
+                        if (smax >= thr) {
+                            unsigned m = 0;
+#pragma unroll
+                            for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
+                            while (m) {
+                                const int j = __ffs(m) - 1;
+                                m &= m - 1;
+                                const int slot = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);
+                                if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + slot) * 8u, (unsigned long long)(unsigned)(first + j));
+                            }
                         }
                     }
                 }
-                float Umine = INFINITY;   // lane b of every warp: bound of point pos+b
-                if (exh) {
-                    // exhaustive scoring of ONE point (validation mode, or a batch cut at its first point)
-                    float x[D];
-                    gsc_lds_row<D>(sb + Ly::X + (unsigned)pos * D * 4, x);
-                    unsigned bd = GSC_NONE, bi = GSC_NONE;
-                    for (int j = 0; j < CPT; ++j) {
-                        float r[D];
-                        gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
-                        const float d = gsc_ann_dist<D>(x, r);
-                        const unsigned b = __float_as_uint(d);
-                        if (d == d && b < bd) { bd = b; bi = (unsigned)(first + j); }   // strict <: lowest index wins
-                    }
-                    const unsigned m = __reduce_min_sync(0xffffffffu, bd);
-                    const unsigned mi = __reduce_min_sync(0xffffffffu, bd == m ? bi : GSC_NONE);
-                    if (lane == 0) gsc_sts_u64(sb + Ly::WKEY + 8u * warp, gsc_pack(m, mi));
-                } else {
-                    if (lane < nb) {
-                        const int p = pos + lane;
-                        const int g = gsc_lds_i(sb + Ly::G + 4u * p);
-                        float x[D], r[D];
-                        gsc_lds_row<D>(sb + Ly::X + (unsigned)p * D * 4, x);
-                        gsc_lds_row<D>(sb + Ly::C + (unsigned)g * D * 4, r);
-                        const float d = gsc_ann_dist<D>(x, r);
-                        Umine = (d == d) ? d : INFINITY;
-                    }
+                __syncthreads();   // ---- bar 1: candidate lists complete ----
+                // ============ phase 1.5: exact keys; warp <-> point, lane <-> slot ============
+                {
+                    constexpr int PW = (B + W - 1) / W;   // points per warp
+                    unsigned long long key[PW];
 #pragma unroll
-                    for (int b = 0; b < B; ++b) {
+                    for (int i = 0; i < PW; ++i) {
+                        const int b = warp + i * W;
+                        key[i] = GSC_KNONE;
                         if (b < nb) {
-                            const int p = pos + b;
-                            const float U = __shfl_sync(0xffffffffu, Umine, b);
-                            const float thr = gsc_lds_f(sb + Ly::HX + 4u * p) - 0.5f * U;   // candidate iff s >= thr (lb <= U)
-                            float xq[DF];
-                            if (DF == 4) {
-                                const float4 t4 = gsc_lds_f4(sb + Ly::X + (unsigned)p * D * 4);
-                                xq[0] = t4.x; xq[1] = t4.y; xq[2] = t4.z; xq[3] = t4.w;
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < DF; ++k) xq[k] = gsc_lds_f(sb + Ly::X + (unsigned)(p * D + k) * 4u);
-                            }
-                            float s[CPT];
-#pragma unroll
-                            for (int j = 0; j < CPT; ++j) s[j] = h[j];
-#pragma unroll
-                            for (int k = 0; k < DF; ++k)
-#pragma unroll
-                                for (int j = 0; j < CPT; ++j) s[j] = fmaf(xq[k], fc[j][k], s[j]);
-                            float smax = s[0];
-#pragma unroll
-                            for (int j = 1; j < CPT; ++j) smax = fmaxf(smax, s[j]);   // NaN-safe: fmaxf ignores NaN
-                            if (smax >= thr) {
-                                unsigned m = 0;
-#pragma unroll
-                                for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
-                                float x[D];
-                                gsc_lds_row<D>(sb + Ly::X + (unsigned)p * D * 4, x);
-                                while (m) {
-                                    const int j = __ffs(m) - 1;
-                                    m &= m - 1;
-                                    float r[D];
-                                    gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
-                                    const float d = gsc_ann_dist<D>(x, r);
-                                    if (d == d) {
-                                        const int slot = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);
-                                        if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + slot) * 8u, gsc_pack(__float_as_uint(d), (unsigned)(first + j)));
-                                    }
-                                }
+                            const int n = min(gsc_lds_i(sb + Ly::LISTN + 4u * b), L);
+                            if (lane < n) {
+                                const unsigned c = (unsigned)gsc_lds_u64(sb + Ly::LIST + (unsigned)(b * L + lane) * 8u);
+                                float x[D], r[D];
+                                gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b) * D * 4, x);
+                                gsc_lds_row<D>(sb + Ly::C + c * D * 4, r);
+                                const float d = gsc_ann_dist<D>(x, r);
+                                if (d == d) key[i] = gsc_pack(__float_as_uint(d), c);
                             }
                         }
                     }
+#pragma unroll
+                    for (int i = 0; i < PW; ++i) {
+                        const int b = warp + i * W;
+                        if (b < nb) {
+                            gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + lane) * 8u, key[i]);
+                            const unsigned long long mk = gsc_warp_min_key(key[i]);
+                            if (lane == 0) gsc_sts_u64(sb + Ly::ABEST + 8u * b, mk);
+                        }
+                    }
                 }
-                __syncthreads();   // ---- bar A: lists / warp keys complete ----
+                __syncthreads();   // ---- bar 2: keys complete ----
                 if (tid == 0) { const unsigned long long t1 = clock64(); c_ph1 += t1 - c_t0; c_t0 = t1; }
-                // ============ phase 2: warp 0 resolves the batch in point order ============
-                if (warp == 0) {
-                    int done = 0;
-                    int wids[B];
-#pragma unroll
-                    for (int t = 0; t < B; ++t) wids[t] = -1;
-                    if (exh) {
-                        unsigned long long k = (lane < W) ? gsc_lds_u64(sb + Ly::WKEY + 8u * lane) : GSC_KNONE;
-                        unsigned kd = gsc_kd(k), ki = gsc_ki(k);
-                        const unsigned m = __reduce_min_sync(0xffffffffu, kd);
-                        const unsigned mi = __reduce_min_sync(0xffffffffu, kd == m ? ki : GSC_NONE);
-                        const int w = (m == GSC_NONE) ? 0 : (int)mi;
-                        const float dwin = (m == GSC_NONE) ? INFINITY : __uint_as_float(m);
-                        float xt[D], r[D];
-                        gsc_lds_row<D>(sb + Ly::X + (unsigned)pos * D * 4, xt);
-                        gsc_lds_row<D>(sb + Ly::C + (unsigned)w * D * 4, r);
-                        const float rate = gsc_lds_f(sb + Ly::RATE + 4u * w);
-#pragma unroll
-                        for (int k2 = 0; k2 < D; ++k2) { float v = xt[k2] - r[k2]; float mm = v * rate; r[k2] = r[k2] + mm; }   // enc:736-740
-                        if (lane == 0) {
-                            gsc_sts_row<D>(sb + Ly::C + (unsigned)w * D * 4, r);
-                            gsc_sts_i(cnt_cur + 4u * w, gsc_lds_i(cnt_cur + 4u * w) + 1);     // enc:744
-                            lab[base + pos] = w;                                              // enc:742
-                            gsc_sts_f(sb + Ly::ET + 4u * pos, sqrtf(dwin / (float)D));        // enc:743 (term)
-                        }
-                        wids[0] = w;
-                        done = 1;
-                    } else {
-                        // lane b < nb: top-2 (distinct ids) of its list, its bound and its point
-                        unsigned long long top1 = GSC_KNONE, top2 = GSC_KNONE;
-                        int nl = 0, over = 0;
-                        float xb[D];
-#pragma unroll
-                        for (int k = 0; k < D; ++k) xb[k] = 0.0f;
-                        if (lane < nb) {
-                            nl = gsc_lds_i(sb + Ly::LISTN + 4u * lane);
-                            over = nl > L;
-                            nl = min(nl, L);
-                            for (int e = 0; e < nl; ++e) {
-                                const unsigned long long k = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
-                                if (k < top1) { top2 = top1; top1 = k; } else if (k < top2) top2 = k;
-                            }
-                            gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + lane) * D * 4, xb);
-                        }
-                        unsigned long long fresh[B];
-#pragma unroll
-                        for (int t = 0; t < B; ++t) fresh[t] = GSC_KNONE;
-#pragma unroll
-                        for (int t = 0; t < B; ++t) {
-                            if (t < nb && done == t) {   // uniform
-                                // ---- lane t: its exact winner under the current state ----
-                                unsigned long long key = GSC_KNONE;
-                                int ok = 0;
-                                if (lane == t) {
-                                    unsigned long long bl = top1;
-                                    bool m1 = false, m2 = false;
-#pragma unroll
-                                    for (int u = 0; u < B; ++u) if (u < t) { m1 |= ((int)gsc_ki(top1) == wids[u]); m2 |= ((int)gsc_ki(top2) == wids[u]); }
-                                    if (m1) {
-                                        bl = top2;
-                                        if (m2 || top2 == GSC_KNONE) {
-                                            // both leaders stale: rescan the list without moved centroids
-                                            bl = GSC_KNONE;
-                                            for (int e = 0; e < nl; ++e) {
-                                                const unsigned long long k = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
-                                                bool mv = false;
-#pragma unroll
-                                                for (int u = 0; u < B; ++u) if (u < t) mv |= ((int)gsc_ki(k) == wids[u]);
-                                                if (!mv && k < bl) bl = k;
-                                            }
-                                        }
-                                    }
-                                    key = bl;
-#pragma unroll
-                                    for (int u = 0; u < B; ++u) if (u < t && fresh[u] < key) key = fresh[u];
-                                    ok = (!over) && (key != GSC_KNONE) && (__uint_as_float(gsc_kd(key)) <= Umine);
-                                }
-                                ok = __shfl_sync(0xffffffffu, ok, t);
-                                if (!ok) { if (__shfl_sync(0xffffffffu, over, t)) ++c_cut_over; else ++c_cut_verify; }
-                                if (ok) {   // uniform
-                                    const int w = (int)__shfl_sync(0xffffffffu, gsc_ki(key), t);
-                                    const unsigned dbits = __shfl_sync(0xffffffffu, gsc_kd(key), t);
-                                    // ---- update the winner (enc:735-744); every lane holds the new row ----
-                                    float xt[D], r[D];
-                                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + t) * D * 4, xt);
-                                    gsc_lds_row<D>(sb + Ly::C + (unsigned)w * D * 4, r);
-                                    const float rate = gsc_lds_f(sb + Ly::RATE + 4u * w);
-#pragma unroll
-                                    for (int k2 = 0; k2 < D; ++k2) { float v = xt[k2] - r[k2]; float mm = v * rate; r[k2] = r[k2] + mm; }
-                                    if (lane == 0) {
-                                        gsc_sts_row<D>(sb + Ly::C + (unsigned)w * D * 4, r);
-                                        gsc_sts_i(cnt_cur + 4u * w, gsc_lds_i(cnt_cur + 4u * w) + 1);
-                                        lab[base + pos + t] = w;
-                                        gsc_sts_f(sb + Ly::ET + 4u * (pos + t), sqrtf(__uint_as_float(dbits) / (float)D));
-                                    }
-                                    __syncwarp();   // the new row is visible to every lane's later reads
-                                    // a centroid moved twice: its older fresh keys are stale
-#pragma unroll
-                                    for (int u = 0; u < B; ++u) if (u < t && wids[u] == w) fresh[u] = GSC_KNONE;
-                                    wids[t] = w;
-                                    // ---- later points score the moved centroid in its new position ----
-                                    if (lane > t && lane < nb) {
-                                        const float dn = gsc_ann_dist<D>(xb, r);
-                                        if (dn == dn) fresh[t] = gsc_pack(__float_as_uint(dn), (unsigned)w);
-                                    }
-                                    done = t + 1;
-                                }
-                            }
-                        }
-                    }
-                    ++c_batches; c_points += done; if (exh) ++c_exh;
-                    if (!exh) { int nn = (lane < nb) ? gsc_lds_i(sb + Ly::LISTN + 4u * lane) : 0; for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o); c_cands += nn; }
-                    // ---- hand over to the next batch ----
-#pragma unroll
-                    for (int t = 0; t < B; ++t) if (lane == 0 && t < done) gsc_sts_i(sb + Ly::MOVED + 4u * t, wids[t]);
-                    if (lane < B) gsc_sts_i(sb + Ly::LISTN + 4u * lane, 0);
-                    if (lane == 0) {
-                        gsc_sts_i(sb + Ly::NMOVED, done);
-                        gsc_sts_i(sb + Ly::POSN, pos + done);
-                        gsc_sts_i(sb + Ly::EXH, done == 0 ? 1 : 0);
-                    }
+                // thread 32 adds the error terms of the previous batch while warp 0 opens this one
+                if (tid == 32 && prev_nb) {
+                    const unsigned eb = sb + Ly::ETB + (unsigned)(((nbatch - 1) & 1) * B) * 4u;
+                    for (int p = 0; p < prev_nb; ++p) e_run += (double)gsc_lds_f(eb + 4u * p);
                 }
-                __syncthreads();   // ---- bar B ----
+                // ============ phase 2: the batch is resolved in rounds ============
+                // warp 0 lane state
+                unsigned long long abest = GSC_KNONE, fresh = GSC_KNONE, key = GSC_KNONE, fkey = GSC_KNONE;
+                int nl = 0, over = 0, t0 = 0, nm = 0, tmax = 0, w = 0, pending = GSC_MODE_DONE, forced = 0;
+                bool act = false;
+                float rn[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) rn[k] = 0.0f;
+                if (warp == 0 && lane < nb) {
+                    nl = gsc_lds_i(sb + Ly::LISTN + 4u * lane);
+                    over = (nl > L) | force_exact;
+                    nl = min(nl, L);
+                    abest = gsc_lds_u64(sb + Ly::ABEST + 8u * lane);
+                    c_cands += nl; c_over += (nl >= L);
+                }
+                const unsigned etb = sb + Ly::ETB + (unsigned)((nbatch & 1) * B) * 4u;
+                for (;;) {
+                    if (warp == 0) {
+                        if (pending == GSC_MODE_SCAN) {
+                            // ---- R3: first conflicting lane, commit the lanes before it ----
+                            unsigned firstc = 32u;
+                            if (lane >= t0 && lane < tmax) {
+                                const unsigned cb = (unsigned)gsc_lds_i(sb + Ly::CB + 4u * lane);
+                                if (cb) firstc = (unsigned)(__ffs(cb) - 1);
+                            }
+                            const int tstar = min(tmax, (int)__reduce_min_sync(FULL, firstc));
+                            const bool commit = lane >= t0 && lane < tstar;
+                            int already = 0;
+                            if (commit) {
+                                gsc_sts_row<D>(sb + Ly::C + (unsigned)w * D * 4, rn);
+                                gsc_sts_i(cnt_cur + 4u * w, gsc_lds_i(cnt_cur + 4u * w) + 1);            // enc:744
+                                lab[base + pos + lane] = w;                                               // enc:742
+                                gsc_sts_f(etb + 4u * lane, sqrtf(__uint_as_float(gsc_kd(key)) / (float)D));  // enc:743 (term)
+                                already = gsc_lds_u8(sb + Ly::MFLAG + (unsigned)w);
+                                gsc_sts_u8(sb + Ly::MFLAG + (unsigned)w, 1);
+                                gsc_sts_i(sb + Ly::MOVED + 4u * (nm + lane - t0), w);
+                                gsc_atoms_or(sb + Ly::DIRTY + 4u * (unsigned)(w / CPT), 1u << (w % CPT));
+                            }
+                            const unsigned anyal = __ballot_sync(FULL, commit && already);
+                            nm += tstar - t0;
+                            __syncwarp();
+                            // unresolved lanes take over the fresh keys of the committed rows
+                            if (lane >= tstar && lane < nb) {
+                                for (int u = t0; u < tstar; ++u) {
+                                    const unsigned long long kk = gsc_lds_u64(sb + Ly::FK + (unsigned)(u * B + lane) * 8u);
+                                    if (kk < fresh) fresh = kk;
+                                }
+                                if (anyal) {
+                                    // a centroid moved twice: older fresh keys may be stale, rebuild from the moved list
+                                    fresh = GSC_KNONE;
+                                    for (int m = 0; m < nm; ++m) {
+                                        const int id = gsc_lds_i(sb + Ly::MOVED + 4u * m);
+                                        float rm[D];
+                                        gsc_lds_row<D>(sb + Ly::C + (unsigned)id * D * 4, rm);
+                                        const float d = gsc_ann_dist<D>(xb, rm);
+                                        if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)id); if (kk < fresh) fresh = kk; }
+                                    }
+                                }
+                                if (abest != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(abest))) {
+                                    // the list leader moved: best key among the entries that did not
+                                    abest = GSC_KNONE;
+                                    for (int e = 0; e < nl; ++e) {
+                                        const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
+                                        if (kk < abest && !gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(kk))) abest = kk;
+                                    }
+                                }
+                            }
+                            t0 = tstar;
+                        } else if (pending == GSC_MODE_REFILTER) {
+                            // exact best key of lane t0: re-filter minimum over the warps, or a moved centroid
+                            unsigned long long k2 = gsc_warp_min_key((lane < W) ? gsc_lds_u64(sb + Ly::WKEY + 8u * lane) : GSC_KNONE);
+                            const unsigned fd = __shfl_sync(FULL, gsc_kd(fresh), t0), fi = __shfl_sync(FULL, gsc_ki(fresh), t0);
+                            const unsigned long long f0 = gsc_pack(fd, fi);
+                            if (f0 < k2) k2 = f0;
+                            if (k2 == GSC_KNONE) k2 = gsc_pack(0x7f800000u, 0u);   // every row NaN: w = 0, d = +inf
+                            fkey = k2;
+                            forced = 1;
+                            ++c_exh;
+                        }
+                        // ---- R1: proposals of the unresolved lanes ----
+                        if (t0 >= nb) {
+                            // hand over to the next batch
+                            if (lane < nm) gsc_sts_u8(sb + Ly::MFLAG + (unsigned)gsc_lds_i(sb + Ly::MOVED + 4u * lane), 0);
+                            gsc_sts_i(sb + Ly::LISTN + 4u * lane, 0);
+                            if (lane == 0) gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
+                            pending = GSC_MODE_DONE;
+                            ++c_batches; c_points += nb;
+                        } else {
+                            ++c_rounds;
+                            bool refilter = false;
+                            if (forced) {
+                                key = (lane == t0) ? fkey : GSC_KNONE;
+                                tmax = t0 + 1;
+                                forced = 0;
+                            } else {
+                                key = abest < fresh ? abest : fresh;
+                                const bool okl = !over && key != GSC_KNONE && __uint_as_float(gsc_kd(key)) <= Umine;
+                                const unsigned bad = __ballot_sync(FULL, lane >= t0 && lane < nb && !okl);
+                                tmax = bad ? (__ffs(bad) - 1) : nb;
+                                refilter = (tmax == t0);
+                            }
+                            if (refilter) {
+                                // lane t0 is not certified: re-filter it against its best known exact distance
+                                if (lane == t0) {
+                                    const float dk = (key != GSC_KNONE && !force_exact) ? __uint_as_float(gsc_kd(key)) : INFINITY;
+                                    gsc_sts_i(sb + Ly::EPOINT, pos + t0);
+                                    gsc_sts_f(sb + Ly::ETHR, gsc_lds_f(sb + Ly::HX + 4u * (pos + t0)) - 0.5f * dk);
+                                    gsc_sts_i(sb + Ly::MODE, GSC_MODE_REFILTER);
+                                }
+                                pending = GSC_MODE_REFILTER;
+                            } else {
+                                // speculative update of every proposing lane (enc:735-740)
+                                act = lane >= t0 && lane < tmax;
+                                w = act ? (int)gsc_ki(key) : 0;
+                                gsc_lds_row<D>(sb + Ly::C + (unsigned)w * D * 4, rn);
+                                const float rate = gsc_lds_f(sb + Ly::RATE + 4u * w);
+#pragma unroll
+                                for (int k2 = 0; k2 < D; ++k2) { float v = xb[k2] - rn[k2]; float mm = v * rate; rn[k2] = rn[k2] + mm; }
+                                gsc_sts_row<D>(sb + Ly::ROWS + (unsigned)lane * D * 4, rn);
+                                gsc_sts_i(sb + Ly::WS + 4u * lane, act ? w : -1);
+                                gsc_sts_u64(sb + Ly::KEYS + 8u * lane, act ? key : GSC_KNONE);
+                                if (lane == 0) { gsc_sts_i(sb + Ly::T0, t0); gsc_sts_i(sb + Ly::TMAX, tmax); gsc_sts_i(sb + Ly::MODE, GSC_MODE_SCAN); }
+                                pending = GSC_MODE_SCAN;
+                            }
+                        }
+                    }
+                    __syncthreads();   // ---- bar 3: proposals / request visible ----
+                    const int mode = gsc_lds_i(sb + Ly::MODE);
+                    if (mode == GSC_MODE_DONE) break;
+                    if (mode == GSC_MODE_SCAN) {
+                        // ---- R2: lane t scores the proposed rows u (warp w takes u = t0+w, t0+w+W, ...) ----
+                        const int s0 = gsc_lds_i(sb + Ly::T0), s1 = gsc_lds_i(sb + Ly::TMAX);
+                        const unsigned long long mykey = gsc_lds_u64(sb + Ly::KEYS + 8u * lane);
+                        const int myw = gsc_lds_i(sb + Ly::WS + 4u * lane);
+                        for (int u = s0 + warp; u < s1; u += W) {
+                            const int wu = gsc_lds_i(sb + Ly::WS + 4u * u);
+                            float ru[D];
+                            gsc_lds_row<D>(sb + Ly::ROWS + (unsigned)u * D * 4, ru);
+                            const float d = gsc_ann_dist<D>(xb, ru);
+                            const unsigned long long kk = (d == d) ? gsc_pack(__float_as_uint(d), (unsigned)wu) : GSC_KNONE;
+                            gsc_sts_u64(sb + Ly::FK + (unsigned)(u * B + lane) * 8u, kk);
+                            const bool conf = (lane > u) && (lane < s1) && ((wu == myw) || (kk < mykey));
+                            const unsigned cb = __ballot_sync(FULL, conf);
+                            if (lane == 0) gsc_sts_i(sb + Ly::CB + 4u * u, (int)cb);
+                        }
+                    } else {
+                        // ---- R2': re-filter ONE point with the whole CTA (exhaustive when the threshold is -inf) ----
+                        const int pe = gsc_lds_i(sb + Ly::EPOINT);
+                        const float thr = gsc_lds_f(sb + Ly::ETHR);
+                        float x[D];
+                        gsc_lds_row<D>(sb + Ly::X + (unsigned)pe * D * 4, x);
+                        float s[CPT];
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) s[j] = h[j];
+#pragma unroll
+                        for (int k = 0; k < DF; ++k)
+#pragma unroll
+                            for (int j = 0; j < CPT; ++j) s[j] = fmaf(x[k], fc[j][k], s[j]);
+                        unsigned m = 0;
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
+                        unsigned long long best = GSC_KNONE;
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            float r[D];
+                            gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
+                            const float d = gsc_ann_dist<D>(x, r);
+                            if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)(first + j)); if (kk < best) best = kk; }
+                        }
+                        best = gsc_warp_min_key(best);
+                        if (lane == 0) gsc_sts_u64(sb + Ly::WKEY + 8u * warp, best);
+                    }
+                    __syncthreads();   // ---- bar 4: round results complete ----
+                }
                 if (tid == 0) c_ph2 += clock64() - c_t0;
-                pos = gsc_lds_i(sb + Ly::POSN);
-            }
-            __syncthreads();  // (E) all terms of the tile written
-            if (tid == 0) {
-                double e = gsc_lds_d(sb + Ly::ERR);                            // enc:743 (Double sum, point order)
-                for (int p = 0; p < tn; ++p) e += (double)gsc_lds_f(sb + Ly::ET + 4u * p);
-                gsc_sts_d(sb + Ly::ERR, e);
-                gsc_sts_i(sb + Ly::POSN, 0);
+                prev_nb = nb;
+                ++nbatch;
             }
         }
         // ---- end of pass: enc:754-761 ----
         __syncthreads();
         for (int j = tid; j < KP; j += T) gsc_sts_i(cnt_prev + 4u * j, 1);
         ++iter;
-        if (tid == 0) {
-            const double e = gsc_lds_d(sb + Ly::ERR);
-            const bool same = (e > prevErr) ? ((e - prevErr) <= tol) : ((prevErr - e) <= tol);
+        if (tid == 32) {
+            if (prev_nb) {
+                const unsigned eb = sb + Ly::ETB + (unsigned)(((nbatch - 1) & 1) * B) * 4u;
+                for (int p = 0; p < prev_nb; ++p) e_run += (double)gsc_lds_f(eb + 4u * p);
+            }
+            gsc_sts_d(sb + Ly::ERR, e_run);
+            const bool same = (e_run > prevErr) ? ((e_run - prevErr) <= tol) : ((prevErr - e_run) <= tol);
             gsc_sts_i(sb + Ly::STOP, (same || iter >= max_passes) ? 1 : 0);
         }
         __syncthreads();
@@ -474,7 +573,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         err_out[f.slot] = gsc_lds_d(sb + Ly::ERR);
         if (dbg) {
             unsigned long long *o = dbg + (long long)f.slot * 8;
-            o[0] = c_batches; o[1] = c_points; o[2] = c_exh; o[3] = c_cut_verify; o[4] = c_cut_over; o[5] = c_cands; o[6] = c_ph1; o[7] = c_ph2;
+            o[0] = c_batches; o[1] = c_points; o[2] = c_exh; o[3] = c_rounds; o[4] = c_over; o[5] = c_cands; o[6] = c_ph1; o[7] = c_ph2;
         }
     }
 }

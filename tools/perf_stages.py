@@ -26,6 +26,6 @@ for K, bits in cfgs:
     print({k: round(v, 2) for k, v in st["stage_ms"].items()})
     cn = ctx.online_counters(min(nf, 8)).astype(float)
     for r in cn[:4]:
-        b, p, e, cv, co, ca = r[:6]
-        print(f"   cycles/batch: phase1 {r[6] / max(b, 1):.0f} phase2 {r[7] / max(b, 1):.0f}")
-        print(f"   batches {b:.0f} points {p:.0f} pts/batch {p / max(b, 1):.2f} exh {e:.0f} cut_verify {cv:.0f} cut_over {co:.0f} cands/pt {ca / max(p, 1):.2f}")
+        b, p, e, rd, ov, ca = r[:6]
+        print(f"   cycles/batch: phase1 {r[6] / max(b, 1):.0f} phase2 {r[7] / max(b, 1):.0f}  cycles/point {(r[6] + r[7]) / max(p, 1):.0f}")
+        print(f"   batches {b:.0f} points {p:.0f} exhaustive {e:.0f} rounds/batch {rd / max(b, 1):.2f} full lists {ov:.0f} cands/pt {ca / max(p, 1):.2f}")
