@@ -228,9 +228,10 @@ void gsc_debug_set_online_exact(int on);
 /* Debug hook: 1 = the seeding kernel evaluates yakmo's sequential float prefix
  * sum with a one-warp serial chain instead of the exact parallel scan. */
 void gsc_debug_set_serial_scan(int on);
-/* Debug: counters of the last online k-means launch, 8 x uint64 per frame:
- * batches, points, exhaustive points, resolver rounds, full candidate lists,
- * candidates scored exactly, phase-1 cycles, phase-2 cycles. */
+/* Debug: counters of the last online k-means launch, 16 x uint64 per frame:
+ * batches, points, re-filtered points, resolver rounds, full candidate lists,
+ * candidates (lane 0), phase-1 cycles, phase-2 cycles, then the phase-1 split:
+ * refresh, filter, barrier wait, exact keys; rest reserved. */
 int gsc_debug_online_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
 
 /* FP32 FFMA throughput probe (roofline denominator for the k-means / search

@@ -188,7 +188,7 @@ class Context:
         self._ck(self.L.gsc_reset_stats(self.h))
 
     def online_counters(self, n_frames: int) -> np.ndarray:
-        out = np.zeros((n_frames, 8), np.uint64)
+        out = np.zeros((n_frames, 16), np.uint64)
         self._ck(self.L.gsc_debug_online_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
 

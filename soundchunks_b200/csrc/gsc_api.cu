@@ -435,7 +435,7 @@ extern "C" void gsc_debug_set_online_exact(int on) { g_force_exact = on ? 1 : 0;
 extern "C" int gsc_debug_online_counters(gsc_ctx *c, unsigned long long *out, int n_frames) {
     if (!c || !out || n_frames > c->F || !c->dbg.p) return set_err(GSC_ERR_ARG, "bad arguments");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(out, c->dbg.p, 64 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out, c->dbg.p, 128 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return GSC_OK;
 }
@@ -450,10 +450,10 @@ static int force_exact_flag() {
 // online k-means; labels buffer must already hold per-point guesses
 static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     TRY(c->passes.ensure(4 * (size_t)c->F)); TRY(c->err.ensure(8 * (size_t)c->F));
-    TRY(c->dbg.ensure(64 * (size_t)c->F));
+    TRY(c->dbg.ensure(128 * (size_t)c->F));
     CU(cudaMemsetAsync(c->passes.p, 0, 4 * (size_t)c->F, c->stream));
     CU(cudaMemsetAsync(c->err.p, 0, 8 * (size_t)c->F, c->stream));
-    CU(cudaMemsetAsync(c->dbg.p, 0, 64 * (size_t)c->F, c->stream));
+    CU(cudaMemsetAsync(c->dbg.p, 0, 128 * (size_t)c->F, c->stream));
     const double tol = int_power10_neg(precision);
     const int K = c->Kmax, fe = force_exact_flag();
     // CTA shape by dictionary size: small K -> small CTAs so that several frames share an SM
@@ -462,7 +462,12 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
         if (K <= 512) return online_launch<8, 8, 64>(c, tol, max_passes, fe);
         if (K <= 1024) return online_launch<8, 8, 128>(c, tol, max_passes, fe);
         if (K <= 2048) return online_launch<8, 16, 128>(c, tol, max_passes, fe);
-        if (K <= 4096) return online_launch<8, 16, 256>(c, tol, max_passes, fe);
+        if (K <= 4096) {
+            static int wide = -1;
+            if (wide < 0) { const char *e = getenv("GSC_ONLINE_T"); wide = (e && atoi(e) == 512) ? 1 : 0; }
+            if (wide) return online_launch<8, 8, 512>(c, tol, max_passes, fe);
+            return online_launch<8, 16, 256>(c, tol, max_passes, fe);
+        }
     } else if (D == 4) {
         if (K <= 256) return online_launch<4, 4, 64>(c, tol, max_passes, fe);
         if (K <= 512) return online_launch<4, 8, 64>(c, tol, max_passes, fe);

@@ -61,7 +61,7 @@
 
 #define GSC_ON_TP 256         // points per shared-memory tile
 #define GSC_ON_B 32           // points per batch (one per lane of the resolving warp)
-#define GSC_ON_L 32           // candidate list capacity per point (one slot per lane)
+#define GSC_ON_L 64           // candidate list capacity per point (W sub-lists of L/W slots, one per warp)
 #define GSC_ON_G 7.62939453125e-06f   // 2^-17
 #define GSC_NONE 0xffffffffu
 #define GSC_KNONE 0xffffffffffffffffull
@@ -143,8 +143,10 @@ struct GscOnLayout {
     static constexpr unsigned HX = X + GSC_ON_TP * D * 4;             // float [TP]
     static constexpr unsigned G = HX + GSC_ON_TP * 4;                 // int   [TP]
     static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [B][L]
-    static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B]
-    static constexpr unsigned ABEST = LISTN + GSC_ON_B * 4;           // u64   [B]
+    static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B][W] entries per (point, warp) sub-list
+    static constexpr unsigned THRW = LISTN + GSC_ON_B * (T / 32) * 4; // float [W][B] candidate thresholds (per-warp copy)
+    static constexpr unsigned OVER = THRW + GSC_ON_B * (T / 32) * 4;  // int   [B] a sub-list overflowed
+    static constexpr unsigned ABEST = OVER + GSC_ON_B * 4;            // u64   [B]
     static constexpr unsigned MOVED = ABEST + GSC_ON_B * 8;           // int   [B]
     static constexpr unsigned ROWS = MOVED + GSC_ON_B * 4;            // float [B][D]
     static constexpr unsigned WS = ROWS + GSC_ON_B * D * 4;           // int   [B]
@@ -184,6 +186,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     constexpr int W = T / 32;
     constexpr int KP = T * CPT;
     constexpr int B = GSC_ON_B, L = GSC_ON_L;
+    constexpr int SL = L / W;                  // slots per (point, warp) sub-list
+    static_assert(L % W == 0 && L % 32 == 0, "list geometry");
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smraw[];
     const unsigned sb = gsc_opaque(gsc_smem_u32(smraw));
@@ -215,14 +219,14 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     for (int j = tid; j < 2 * KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
     for (int j = tid; j < KP / 4; j += T) gsc_sts_i(sb + Ly::MFLAG + 4u * j, 0);
     gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
-    if (tid < B) gsc_sts_i(sb + Ly::LISTN + 4u * tid, 0);
+    for (int j = tid; j < B * W; j += T) gsc_sts_i(sb + Ly::LISTN + 4u * j, 0);
     if (tid == 0) {
         gsc_sts_d(sb + Ly::ERR, 3.40282346638528860e+38);
         gsc_sts_i(sb + Ly::STOP, 0); gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
     }
     __syncthreads();
 
-    unsigned long long c_ph1 = 0, c_ph2 = 0, c_t0 = 0;
+    unsigned long long c_ph1 = 0, c_ph2 = 0, c_t0 = 0, c_p0 = 0, c_flt = 0, c_b1 = 0, c_15 = 0, c_tx = 0;
     unsigned long long c_batches = 0, c_exh = 0, c_rounds = 0, c_over = 0, c_points = 0, c_cands = 0;
     int iter = 0;
     for (;;) {
@@ -273,6 +277,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                             }
                     }
                 }
+                if (tid == 0) { c_tx = clock64(); c_p0 += c_tx - c_t0; }
                 // ============ phase 1: all warps, codebook frozen ============
                 float xb[D];              // lane b of every warp: point pos+b
                 float Umine = INFINITY;   // ... and its bound
@@ -287,74 +292,90 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const float d = gsc_ann_dist<D>(xb, r);
                     Umine = (d == d) ? d * slack : INFINITY;   // any number is a valid threshold; see phase 2
                 }
-                if (!force_exact) {
-#pragma unroll 2
-                    for (int b = 0; b < nb; ++b) {
-                        const int p = pos + b;
-                        const float U = __shfl_sync(FULL, Umine, b);
-                        const float thr = gsc_lds_f(sb + Ly::HX + 4u * p) - 0.5f * U;   // candidate iff s >= thr (lb <= U)
-                        float xq[DF];
-                        if (DF == 4) {
-                            const float4 t4 = gsc_lds_f4(sb + Ly::X + (unsigned)p * D * 4);
-                            xq[0] = t4.x; xq[1] = t4.y; xq[2] = t4.z; xq[3] = t4.w;
-                        } else {
+                // pass (a): branch-free filter over the 32 points -> one hit bit per (thread, point)
+                gsc_sts_f(sb + Ly::THRW + (unsigned)(warp * B + lane) * 4u,
+                          (lane < nb && !force_exact) ? gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * Umine : INFINITY);
+                __syncwarp();
+                unsigned hit = 0;
+#pragma unroll 4
+                for (int b = 0; b < B; ++b) {
+                    const float thr = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b) * 4u);   // candidate iff s >= thr (lb <= U)
+                    const float4 t4 = gsc_lds_f4(sb + Ly::X + (unsigned)(pos + b) * D * 4);
+                    const float xq[4] = {t4.x, t4.y, t4.z, t4.w};
+                    float s[CPT];
 #pragma unroll
-                            for (int k = 0; k < DF; ++k) xq[k] = gsc_lds_f(sb + Ly::X + (unsigned)(p * D + k) * 4u);
-                        }
-                        float s[CPT];
+                    for (int j = 0; j < CPT; ++j) s[j] = h[j];
 #pragma unroll
-                        for (int j = 0; j < CPT; ++j) s[j] = h[j];
+                    for (int k = 0; k < DF; ++k)
 #pragma unroll
-                        for (int k = 0; k < DF; ++k)
+                        for (int j = 0; j < CPT; ++j) s[j] = fmaf(xq[k], fc[j][k], s[j]);
+                    float smax = s[0];
 #pragma unroll
-                            for (int j = 0; j < CPT; ++j) s[j] = fmaf(xq[k], fc[j][k], s[j]);
-                        float smax = s[0];
+                    for (int j = 1; j < CPT; ++j) smax = fmaxf(smax, s[j]);   // NaN-safe: fmaxf ignores NaN
+                    hit |= (smax >= thr) ? (1u << b) : 0u;
+                }
+                // pass (b): expand the hits: which centroids, exact distance, key into the warp's sub-list
+                while (hit) {
+                    const int b = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    const float thr = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b) * 4u);
+                    float x[D];
+                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b) * D * 4, x);
+                    float s[CPT];
 #pragma unroll
-                        for (int j = 1; j < CPT; ++j) smax = fmaxf(smax, s[j]);   // NaN-safe: fmaxf ignores NaN
-                        if (smax >= thr) {
-                            unsigned m = 0;
+                    for (int j = 0; j < CPT; ++j) s[j] = h[j];
 #pragma unroll
-                            for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
-                            while (m) {
-                                const int j = __ffs(m) - 1;
-                                m &= m - 1;
-                                const int slot = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);
-                                if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + slot) * 8u, (unsigned long long)(unsigned)(first + j));
-                            }
+                    for (int k = 0; k < DF; ++k)
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) s[j] = fmaf(x[k], fc[j][k], s[j]);
+                    unsigned m = 0;
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        float r[D];
+                        gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
+                        const float d = gsc_ann_dist<D>(x, r);
+                        if (d == d) {
+                            const int slot = gsc_atoms_add(sb + Ly::LISTN + (unsigned)(b * W + warp) * 4u, 1);
+                            if (slot < SL)
+                                gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + warp * SL + slot) * 8u, gsc_pack(__float_as_uint(d), (unsigned)(first + j)));
                         }
                     }
                 }
+                if (tid == 0) { const unsigned long long t1 = clock64(); c_flt += t1 - c_tx; c_tx = t1; }
                 __syncthreads();   // ---- bar 1: candidate lists complete ----
-                // ============ phase 1.5: exact keys; warp <-> point, lane <-> slot ============
+                if (tid == 0) { const unsigned long long t1 = clock64(); c_b1 += t1 - c_tx; c_tx = t1; }
+                // ============ phase 1.5: warp <-> point: close the sub-lists, best key of the point ============
                 {
                     constexpr int PW = (B + W - 1) / W;   // points per warp
-                    unsigned long long key[PW];
 #pragma unroll
                     for (int i = 0; i < PW; ++i) {
                         const int b = warp + i * W;
-                        key[i] = GSC_KNONE;
-                        if (b < nb) {
-                            const int n = min(gsc_lds_i(sb + Ly::LISTN + 4u * b), L);
-                            if (lane < n) {
-                                const unsigned c = (unsigned)gsc_lds_u64(sb + Ly::LIST + (unsigned)(b * L + lane) * 8u);
-                                float x[D], r[D];
-                                gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b) * D * 4, x);
-                                gsc_lds_row<D>(sb + Ly::C + c * D * 4, r);
-                                const float d = gsc_ann_dist<D>(x, r);
-                                if (d == d) key[i] = gsc_pack(__float_as_uint(d), c);
+                        if (b < nb) {   // uniform per warp
+                            const int cw = (lane < W) ? gsc_lds_i(sb + Ly::LISTN + (unsigned)(b * W + lane) * 4u) : 0;
+                            if (lane < W) gsc_sts_i(sb + Ly::LISTN + (unsigned)(b * W + lane) * 4u, 0);
+                            const unsigned ov = __ballot_sync(FULL, cw > SL);
+                            unsigned long long mk = GSC_KNONE;
+#pragma unroll
+                            for (int q = 0; q < L / 32; ++q) {
+                                const int slot = lane + 32 * q;
+                                const int cnt = __shfl_sync(FULL, cw, slot / SL);
+                                const unsigned sa = sb + Ly::LIST + (unsigned)(b * L + slot) * 8u;
+                                if ((slot % SL) < cnt) { const unsigned long long kk = gsc_lds_u64(sa); if (kk < mk) mk = kk; }
+                                else gsc_sts_u64(sa, GSC_KNONE);
                             }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < PW; ++i) {
-                        const int b = warp + i * W;
-                        if (b < nb) {
-                            gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + lane) * 8u, key[i]);
-                            const unsigned long long mk = gsc_warp_min_key(key[i]);
-                            if (lane == 0) gsc_sts_u64(sb + Ly::ABEST + 8u * b, mk);
+                            mk = gsc_warp_min_key(mk);
+                            if (lane == 0) {
+                                gsc_sts_u64(sb + Ly::ABEST + 8u * b, mk);
+                                gsc_sts_i(sb + Ly::OVER + 4u * b, ov ? 1 : 0);
+                            }
+                            if (warp == 0) { int tot = cw; for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o); c_cands += tot; c_over += ov ? 1 : 0; }
                         }
                     }
                 }
+                if (tid == 0) { const unsigned long long t1 = clock64(); c_15 += t1 - c_tx; c_tx = t1; }
                 __syncthreads();   // ---- bar 2: keys complete ----
                 if (tid == 0) { const unsigned long long t1 = clock64(); c_ph1 += t1 - c_t0; c_t0 = t1; }
                 // thread 32 adds the error terms of the previous batch while warp 0 opens this one
@@ -365,17 +386,14 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                 // ============ phase 2: the batch is resolved in rounds ============
                 // warp 0 lane state
                 unsigned long long abest = GSC_KNONE, fresh = GSC_KNONE, key = GSC_KNONE, fkey = GSC_KNONE;
-                int nl = 0, over = 0, t0 = 0, nm = 0, tmax = 0, w = 0, pending = GSC_MODE_DONE, forced = 0;
+                int over = 0, t0 = 0, nm = 0, tmax = 0, w = 0, pending = GSC_MODE_DONE, forced = 0;
                 bool act = false;
                 float rn[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) rn[k] = 0.0f;
                 if (warp == 0 && lane < nb) {
-                    nl = gsc_lds_i(sb + Ly::LISTN + 4u * lane);
-                    over = (nl > L) | force_exact;
-                    nl = min(nl, L);
+                    over = gsc_lds_i(sb + Ly::OVER + 4u * lane) | force_exact;
                     abest = gsc_lds_u64(sb + Ly::ABEST + 8u * lane);
-                    c_cands += nl; c_over += (nl >= L);
                 }
                 const unsigned etb = sb + Ly::ETB + (unsigned)((nbatch & 1) * B) * 4u;
                 for (;;) {
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 if (abest != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(abest))) {
                                     // the list leader moved: best key among the entries that did not
                                     abest = GSC_KNONE;
-                                    for (int e = 0; e < nl; ++e) {
+                                    for (int e = 0; e < L; ++e) {
                                         const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
                                         if (kk < abest && !gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(kk))) abest = kk;
                                     }
@@ -445,7 +463,6 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         if (t0 >= nb) {
                             // hand over to the next batch
                             if (lane < nm) gsc_sts_u8(sb + Ly::MFLAG + (unsigned)gsc_lds_i(sb + Ly::MOVED + 4u * lane), 0);
-                            gsc_sts_i(sb + Ly::LISTN + 4u * lane, 0);
                             if (lane == 0) gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
                             pending = GSC_MODE_DONE;
                             ++c_batches; c_points += nb;
@@ -572,8 +589,9 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         passes_out[f.slot] = iter;
         err_out[f.slot] = gsc_lds_d(sb + Ly::ERR);
         if (dbg) {
-            unsigned long long *o = dbg + (long long)f.slot * 8;
+            unsigned long long *o = dbg + (long long)f.slot * 16;
             o[0] = c_batches; o[1] = c_points; o[2] = c_exh; o[3] = c_rounds; o[4] = c_over; o[5] = c_cands; o[6] = c_ph1; o[7] = c_ph2;
+            o[8] = c_p0; o[9] = c_flt; o[10] = c_b1; o[11] = c_15;
         }
     }
 }
