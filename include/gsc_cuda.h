@@ -19,7 +19,7 @@
  * MXCSR is saved, masked and restored around every entry because the
  * FreePascal host runs with FP exceptions unmasked.
  *
- * Layouts (shared with oracle/gsc_oracle.h):
+ * Layouts:
  *   pcm       int16 planar [C][S]  (row stride in samples)
  *   chunk n   = i*C + ch, cs samples                      enc:475-484
  *   attr      bit0 Reversed | bit1 Negative               enc:960-961
@@ -150,8 +150,10 @@ int gsc_assign(gsc_ctx *ctx, const float *X, int N, int D,
                const float *centroids, int K, int32_t *labels, float *dist);
 
 /* enc:843-889: class means in the sample domain, population sort (FreePascal
- * quicksort order), dictionary quantisation.  Outputs as in
- * gsc_ref_build_dictionary; any may be NULL. */
+ * quicksort order), dictionary quantisation.  means float[K][cs] and
+ * counts/order int32[K] in dictionary order (order[i] = cluster of entry i),
+ * dict int16[K][cs], datten/dattr uint8[K], entry int32[N] (dictionary entry
+ * of every chunk's cluster); any output may be NULL. */
 int gsc_build_dictionary(gsc_ctx *ctx, const int32_t *labels, const int16_t *pcm,
                          int64_t stride, int C, int S, const uint8_t *attr,
                          int cs, int K, int bits, int divider, float *means,

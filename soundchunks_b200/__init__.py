@@ -6,3 +6,4 @@ bitstream writer stay on the host) and the cluster.py-compatible shim.
 """
 from .binding import (Context, FrameResult, GscError, LegacyAnn, Params, default_params, device_count,  # noqa: F401
                       legacy_yakmo, load_library, EXPORTS, SO_PATH)
+from . import host  # noqa: E402,F401  (libgsc_host.so: planner, .gsc writer/decoder, multi-GPU scheduler)

@@ -44,5 +44,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+def build_host(force: bool = False) -> str:
+    """libgsc_host.so + gsc_encode / gsc_decode (host/Makefile, g++ only)."""
+    host = os.path.join(os.path.dirname(HERE), "host")
+    out = os.path.join(host, "_build", "libgsc_host.so")
+    build(force=False)
+    r = subprocess.run(["make", "-C", host, "-s"] + (["-B"] if force else []), capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building the host library failed")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))
