@@ -24,7 +24,7 @@ EXPORTS = [
     "gsc_last_error", "gsc_device_count", "gsc_create", "gsc_destroy", "gsc_ctx_device", "gsc_ctx_stream",
     "gsc_synchronize", "gsc_get_stats", "gsc_reset_stats",
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
-    "gsc_assign", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
+    "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
     "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters",
 ]
@@ -247,6 +247,26 @@ class Context:
         N, D = X.shape
         labels = np.zeros(N, np.int32)
         self._ck(self.L.gsc_lloyd(C.c_void_p(self.h), _vp(X), N, D, _vp(cen), cen.shape[0], iters, _vp(labels)))
+        return cen, labels
+
+    # ---- oversized frame split over GPUs (one Context per rank) ------------
+    def split_begin(self, X, centroids):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        cen = np.ascontiguousarray(centroids, dtype=np.float32)
+        self._split = (X.shape[0], X.shape[1], cen.shape[0])
+        self._ck(self.L.gsc_split_begin(C.c_void_p(self.h), _vp(X), X.shape[0], X.shape[1], _vp(cen), cen.shape[0]))
+
+    def split_step(self, acc_dev_ptr: int):
+        self._ck(self.L.gsc_split_step(C.c_void_p(self.h), C.c_void_p(acc_dev_ptr)))
+
+    def split_update(self, acc_dev_ptr: int):
+        self._ck(self.L.gsc_split_update(C.c_void_p(self.h), C.c_void_p(acc_dev_ptr)))
+
+    def split_end(self):
+        N, D, K = self._split
+        cen = np.zeros((K, D), np.float32)
+        labels = np.zeros(N, np.int32)
+        self._ck(self.L.gsc_split_end(C.c_void_p(self.h), _vp(cen), _vp(labels)))
         return cen, labels
 
     def assign(self, X, centroids):

@@ -707,6 +707,49 @@ extern "C" int gsc_lloyd(gsc_ctx *c, const float *X, int N, int D, float *centro
     return sync(c);
 }
 
+// ---- oversized single frame split by points over several GPUs (BASELINE.json configs[3]) ----
+extern "C" int gsc_split_begin(gsc_ctx *c, const float *X, int N, int D, const float *centroids, int K) {
+    FpGuard g;
+    if (!c || !centroids) return set_err(GSC_ERR_ARG, "null argument");
+    TRY(upload_points(c, X, N, D, K));
+    TRY(c->cen.ensure(4 * (size_t)K * D));
+    TRY(h2d(c, c->cen.p, centroids, 4 * (size_t)K * D));
+    c->cs = D;   // remembers D for the following split calls
+    return sync(c);
+}
+extern "C" int gsc_split_step(gsc_ctx *c, float *acc_dev) {
+    FpGuard g;
+    if (!c || !acc_dev || c->F != 1) return set_err(GSC_ERR_ARG, "gsc_split_step: call gsc_split_begin first");
+    CU(cudaSetDevice(c->device));
+    const int D = c->cs, K = c->Kmax;
+    TRY(stage_assign(c, D, false));
+    const size_t fk = (size_t)K;
+    TRY(c->sums.ensure(4 * fk * D)); TRY(c->cnt0.ensure(4 * fk));
+    dim3 g2((K + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, 1);
+    DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
+                         c->labels.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), K));
+    DISPATCH_D(D, LAUNCH(c, k_pack_acc<D>, (K + 255) / 256, 256, 0, c->sums.as<float>(), c->cnt0.as<int>(), acc_dev, K));
+    return sync(c);
+}
+extern "C" int gsc_split_update(gsc_ctx *c, const float *acc_dev) {
+    FpGuard g;
+    if (!c || !acc_dev || c->F != 1) return set_err(GSC_ERR_ARG, "gsc_split_update: call gsc_split_begin first");
+    CU(cudaSetDevice(c->device));
+    const int D = c->cs, K = c->Kmax;
+    DISPATCH_D(D, LAUNCH(c, k_means_from_acc<D>, (K + 255) / 256, 256, 0, acc_dev, c->cen.as<float>(), K));
+    return sync(c);
+}
+extern "C" int gsc_split_end(gsc_ctx *c, float *centroids, int32_t *labels) {
+    FpGuard g;
+    if (!c || c->F != 1) return set_err(GSC_ERR_ARG, "gsc_split_end: call gsc_split_begin first");
+    CU(cudaSetDevice(c->device));
+    const int D = c->cs, K = c->Kmax;
+    TRY(stage_assign(c, D, false));
+    if (centroids) TRY(d2h(c, centroids, c->cen.p, 4 * (size_t)K * D));
+    if (labels) TRY(d2h(c, labels, c->labels.p, 4 * (size_t)c->sumN));
+    return sync(c);
+}
+
 extern "C" int gsc_build_dictionary(gsc_ctx *c, const int32_t *labels, const int16_t *pcm, int64_t stride, int C, int S,
                                     const uint8_t *attr, int cs, int K, int bits, int divider, float *means,
                                     int32_t *order, int32_t *counts, int16_t *dict, uint8_t *datten, uint8_t *dattr,

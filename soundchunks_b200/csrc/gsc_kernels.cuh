@@ -567,6 +567,28 @@ __global__ void k_means_from_sums(const GscFrame *__restrict__ frames, const flo
     for (int k = 0; k < D; ++k) cen[o + k] = sums[o + k] / fc;
 }
 
+// Oversized-frame split: pack this rank's owner sums and counts into the
+// all-reduce buffer acc[K][D+1] (D sums, then the count as a float: exact below 2^24), and
+// turn the reduced buffer back into centroids (empty clusters keep theirs).
+template <int D>
+__global__ void k_pack_acc(const float *__restrict__ sums, const int *__restrict__ counts,
+                           float *__restrict__ acc, int K) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[(long long)c * (D + 1) + k] = sums[(long long)c * D + k];
+    acc[(long long)c * (D + 1) + D] = (float)counts[c];
+}
+template <int D>
+__global__ void k_means_from_acc(const float *__restrict__ acc, float *__restrict__ cen, int K) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    const float n = acc[(long long)c * (D + 1) + D];
+    if (!(n > 0.0f)) return;
+#pragma unroll
+    for (int k = 0; k < D; ++k) cen[(long long)c * D + k] = acc[(long long)c * (D + 1) + k] / n;
+}
+
 // MODE 2: class means in the sample domain (enc:845-864), Double accumulate,
 // Single store via div0.
 template <int CS>

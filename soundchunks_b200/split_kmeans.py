@@ -29,3 +29,21 @@ def lloyd_split(partial: Callable, centroids: np.ndarray, iters: int, dist=None,
         nz = cnt > 0
         cen[nz] = (a[nz, :-1] / cnt[nz, None]).astype(np.float32)
     return cen
+
+
+def lloyd_split_gpu(ctx, X_shard: np.ndarray, centroids: np.ndarray, iters: int, dist=None):
+    """The device path: this rank's shard lives in `ctx` (libgsc_cuda), the K x (D+1) partial sums
+    are written straight into a torch CUDA tensor and all-reduced by NCCL over NVLink; the division
+    runs on the device.  Returns (centroids, labels of this shard) after a final assignment."""
+    import torch
+    K, D = np.asarray(centroids).shape
+    ctx.split_begin(X_shard, centroids)
+    acc = torch.empty((K, D + 1), dtype=torch.float32, device=torch.device("cuda", ctx.device))
+    multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
+    for _ in range(iters):
+        ctx.split_step(acc.data_ptr())              # returns with the library stream idle
+        if multi:
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            torch.cuda.synchronize(acc.device)
+        ctx.split_update(acc.data_ptr())
+    return ctx.split_end()
