@@ -141,22 +141,24 @@ int gsc_knn_scan_reduce(gsc_ctx *ctx, const float *X, int N, int D,
                         int32_t *labels, int *passes, double *err);
 
 /* Plain batch Lloyd (BASELINE.json's 1e-4 centroid contract): `iters` x
- * (exact assign, mean), then a final assign.  centroids in/out. */
+ * (exact assign, mean), then a final assign.  centroids in/out.  Member rows
+ * are accumulated in Double and the mean is rounded to Single once, so the
+ * result does not depend on the summation order (see gsc_split_*). */
 int gsc_lloyd(gsc_ctx *ctx, const float *X, int N, int D, float *centroids,
               int K, int iters, int32_t *labels);
 
 /* Oversized single frame (BASELINE.json configs[3]): the points of
  * ONE frame are split over several GPUs, one context per GPU holding a shard.
  * Per Lloyd iteration: gsc_split_step writes this shard's partial sums into
- * acc_dev, float[K][D+1] in DEVICE memory owned by the caller (D sums, then the
- * member count); the caller all-reduces acc_dev over the ranks (NCCL); then
+ * acc_dev, double[K][D+1] in DEVICE memory owned by the caller (D sums, then
+ * the member count); the caller all-reduces acc_dev over the ranks (NCCL); then
  * gsc_split_update turns the reduced buffer into the new centroids (empty
  * clusters keep theirs).  Every call returns with the context stream idle; the
  * caller synchronises its own collective before gsc_split_update. */
 int gsc_split_begin(gsc_ctx *ctx, const float *X, int N, int D,
                     const float *centroids, int K);
-int gsc_split_step(gsc_ctx *ctx, float *acc_dev);
-int gsc_split_update(gsc_ctx *ctx, const float *acc_dev);
+int gsc_split_step(gsc_ctx *ctx, double *acc_dev);
+int gsc_split_update(gsc_ctx *ctx, const double *acc_dev);
 /* final assignment against the last centroids; both outputs optional */
 int gsc_split_end(gsc_ctx *ctx, float *centroids, int32_t *labels);
 

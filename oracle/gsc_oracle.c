@@ -550,25 +550,30 @@ int gsc_ref_knn_scan_reduce(const float *X, int N, int D, float *centroids,
                                            max_passes, 1, labels, err_out);
 }
 
-/* Plain batch Lloyd (the 1e-4 centroid contract of BASELINE.json). */
+/* Plain batch Lloyd (the 1e-4 centroid contract of BASELINE.json).  There is no
+ * Lloyd in the reference to follow (enc:824 calls yakmo with maxIter = 0), so the
+ * arithmetic is ours: member rows are accumulated in Double and the mean is
+ * rounded to Single once, which makes the result independent of the summation
+ * order (up to a ~1e-9 chance per coordinate) -- the property the multi-GPU
+ * split of one frame needs. */
 void gsc_ref_lloyd(const float *X, int N, int D, float *centroids, int K,
                    int iters, int32_t *labels)
 {
-    float *sum = (float *)malloc(sizeof(float) * (size_t)K * D);
+    double *sum = (double *)malloc(sizeof(double) * (size_t)K * D);
     int32_t *cnt = (int32_t *)malloc(sizeof(int32_t) * K);
     for (int it = 0; it < iters; ++it) {
         gsc_ref_assign(X, N, D, centroids, K, labels, NULL);
-        memset(sum, 0, sizeof(float) * (size_t)K * D);
+        memset(sum, 0, sizeof(double) * (size_t)K * D);
         memset(cnt, 0, sizeof(int32_t) * K);
         for (int j = 0; j < N; ++j) {
-            float *s = sum + (size_t)labels[j] * D;
-            for (int k = 0; k < D; ++k) s[k] = s[k] + X[(size_t)j * D + k];
+            double *s = sum + (size_t)labels[j] * D;
+            for (int k = 0; k < D; ++k) s[k] = s[k] + (double)X[(size_t)j * D + k];
             cnt[labels[j]]++;
         }
         for (int c = 0; c < K; ++c)
             if (cnt[c] > 0)
                 for (int k = 0; k < D; ++k)
-                    centroids[(size_t)c * D + k] = sum[(size_t)c * D + k] / (float)cnt[c];
+                    centroids[(size_t)c * D + k] = (float)(sum[(size_t)c * D + k] / (double)cnt[c]);
     }
     gsc_ref_assign(X, N, D, centroids, K, labels, NULL);
     free(sum); free(cnt);

@@ -385,16 +385,22 @@ static int stage_assign(gsc_ctx *c, int D, bool want_dist) {
     return GSC_OK;
 }
 
-static int stage_lloyd_update(gsc_ctx *c, int D) {
-    const size_t fk = (size_t)c->F * c->Kmax;
-    TRY(c->sums.ensure(4 * fk * D)); TRY(c->cnt0.ensure(4 * fk));
+// Lloyd update into `acc` (Double [F][Kmax][D+1]; default: the context's own buffer), then means.
+static int stage_lloyd_sums(gsc_ctx *c, int D, double *acc) {
     dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
-    DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
-                         c->labels.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), c->Kmax));
-    dim3 g3((c->Kmax + 255) / 256, c->F);
-    DISPATCH_D(D, LAUNCH(c, k_means_from_sums<D>, g3, 256, 0, c->frames.as<GscFrame>(), c->sums.as<float>(),
-                         c->cnt0.as<int>(), c->cen.as<float>(), c->Kmax, 1));
+    DISPATCH_D(D, LAUNCH(c, k_owner_sums_d<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
+                         c->labels.as<int>(), acc, c->Kmax));
     return GSC_OK;
+}
+static int stage_lloyd_means(gsc_ctx *c, int D, const double *acc) {
+    dim3 g3((c->Kmax + 255) / 256, c->F);
+    DISPATCH_D(D, LAUNCH(c, k_means_from_acc<D>, g3, 256, 0, c->frames.as<GscFrame>(), acc, c->cen.as<float>(), c->Kmax));
+    return GSC_OK;
+}
+static int stage_lloyd_update(gsc_ctx *c, int D) {
+    TRY(c->sums.ensure(8 * (size_t)c->F * c->Kmax * (D + 1)));
+    TRY(stage_lloyd_sums(c, D, c->sums.as<double>()));
+    return stage_lloyd_means(c, D, c->sums.as<double>());
 }
 
 // Slack on the candidate threshold of the online kernel (a tuning knob: any value gives the same
@@ -717,26 +723,20 @@ extern "C" int gsc_split_begin(gsc_ctx *c, const float *X, int N, int D, const f
     c->cs = D;   // remembers D for the following split calls
     return sync(c);
 }
-extern "C" int gsc_split_step(gsc_ctx *c, float *acc_dev) {
+extern "C" int gsc_split_step(gsc_ctx *c, double *acc_dev) {
     FpGuard g;
     if (!c || !acc_dev || c->F != 1) return set_err(GSC_ERR_ARG, "gsc_split_step: call gsc_split_begin first");
     CU(cudaSetDevice(c->device));
-    const int D = c->cs, K = c->Kmax;
+    const int D = c->cs;
     TRY(stage_assign(c, D, false));
-    const size_t fk = (size_t)K;
-    TRY(c->sums.ensure(4 * fk * D)); TRY(c->cnt0.ensure(4 * fk));
-    dim3 g2((K + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, 1);
-    DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
-                         c->labels.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), K));
-    DISPATCH_D(D, LAUNCH(c, k_pack_acc<D>, (K + 255) / 256, 256, 0, c->sums.as<float>(), c->cnt0.as<int>(), acc_dev, K));
+    TRY(stage_lloyd_sums(c, D, acc_dev));
     return sync(c);
 }
-extern "C" int gsc_split_update(gsc_ctx *c, const float *acc_dev) {
+extern "C" int gsc_split_update(gsc_ctx *c, const double *acc_dev) {
     FpGuard g;
     if (!c || !acc_dev || c->F != 1) return set_err(GSC_ERR_ARG, "gsc_split_update: call gsc_split_begin first");
     CU(cudaSetDevice(c->device));
-    const int D = c->cs, K = c->Kmax;
-    DISPATCH_D(D, LAUNCH(c, k_means_from_acc<D>, (K + 255) / 256, 256, 0, acc_dev, c->cen.as<float>(), K));
+    TRY(stage_lloyd_means(c, c->cs, acc_dev));
     return sync(c);
 }
 extern "C" int gsc_split_end(gsc_ctx *c, float *centroids, int32_t *labels) {

@@ -567,26 +567,60 @@ __global__ void k_means_from_sums(const GscFrame *__restrict__ frames, const flo
     for (int k = 0; k < D; ++k) cen[o + k] = sums[o + k] / fc;
 }
 
-// Oversized-frame split: pack this rank's owner sums and counts into the
-// all-reduce buffer acc[K][D+1] (D sums, then the count as a float: exact below 2^24), and
-// turn the reduced buffer back into centroids (empty clusters keep theirs).
+// Lloyd update: member rows accumulated in Double, mean rounded to Single once, so the result
+// does not depend on the summation order (single GPU, or per-rank partial sums + all-reduce).
 template <int D>
-__global__ void k_pack_acc(const float *__restrict__ sums, const int *__restrict__ counts,
-                           float *__restrict__ acc, int K) {
+__global__ void __launch_bounds__(GSC_OWNER_THREADS) k_owner_sums_d(const GscFrame *__restrict__ frames,
+                                                                    const float *__restrict__ X,
+                                                                    const int *__restrict__ labels,
+                                                                    double *__restrict__ acc,   // [F][Kmax][D+1]: D sums, count
+                                                                    int Kmax) {
+    __shared__ int s_lab[GSC_OWNER_TILE];
+    const GscFrame f = frames[blockIdx.y];
+    if (f.K <= 0) return;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= K) return;
+    if (blockIdx.x * blockDim.x >= f.K) return;
+    const float *Xf = X + f.chunk_off * D;
+    const int *lab = labels + f.chunk_off;
+    double sum[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) acc[(long long)c * (D + 1) + k] = sums[(long long)c * D + k];
-    acc[(long long)c * (D + 1) + D] = (float)counts[c];
+    for (int k = 0; k < D; ++k) sum[k] = 0.0;
+    int cnt = 0;
+    for (int base = 0; base < f.N; base += GSC_OWNER_TILE) {
+        const int lim = min(GSC_OWNER_TILE, f.N - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < lim; t += blockDim.x) s_lab[t] = lab[base + t];
+        __syncthreads();
+        for (int t = 0; t < lim; ++t) {
+            if (s_lab[t] == c) {
+                float p[D];
+                gsc_load_row<D>(Xf, base + t, p);
+#pragma unroll
+                for (int k = 0; k < D; ++k) sum[k] += (double)p[k];
+                ++cnt;
+            }
+        }
+    }
+    if (c < f.K) {
+        double *o = acc + ((long long)f.slot * Kmax + c) * (D + 1);
+#pragma unroll
+        for (int k = 0; k < D; ++k) o[k] = sum[k];
+        o[D] = (double)cnt;
+    }
 }
+// centroid = Single(sum / count); empty clusters keep theirs.  acc may be the all-reduced buffer.
 template <int D>
-__global__ void k_means_from_acc(const float *__restrict__ acc, float *__restrict__ cen, int K) {
+__global__ void k_means_from_acc(const GscFrame *__restrict__ frames, const double *__restrict__ acc,
+                                 float *__restrict__ cen, int Kmax) {
+    const GscFrame f = frames[blockIdx.y];
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= K) return;
-    const float n = acc[(long long)c * (D + 1) + D];
-    if (!(n > 0.0f)) return;
+    if (c >= f.K) return;
+    const double *a = acc + ((long long)f.slot * Kmax + c) * (D + 1);
+    const double n = a[D];
+    if (!(n > 0.0)) return;
+    float *o = cen + ((long long)f.slot * Kmax + c) * D;
 #pragma unroll
-    for (int k = 0; k < D; ++k) cen[(long long)c * D + k] = acc[(long long)c * (D + 1) + k] / n;
+    for (int k = 0; k < D; ++k) o[k] = (float)(a[k] / n);
 }
 
 // MODE 2: class means in the sample domain (enc:845-864), Double accumulate,

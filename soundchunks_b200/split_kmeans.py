@@ -15,7 +15,7 @@ def lloyd_split(partial: Callable, centroids: np.ndarray, iters: int, dist=None,
     """Generic driver.  `partial(cen)` -> tensor [K][D+1] of THIS rank's sums and counts for the
     current centroids (host array or device tensor); the tensor is all-reduced in place.
     `update(acc)` (optional) consumes the reduced tensor on the device; without it the division
-    happens here in float32: mean = sum / count, empty clusters keep their centroid."""
+    happens here: mean = Single(sum / count) in Double, empty clusters keep their centroid."""
     cen = np.array(centroids, dtype=np.float32, copy=True)
     for _ in range(iters):
         acc = partial(cen)
@@ -24,7 +24,7 @@ def lloyd_split(partial: Callable, centroids: np.ndarray, iters: int, dist=None,
         if update is not None:
             cen = update(acc)
             continue
-        a = acc.detach().cpu().numpy() if hasattr(acc, "detach") else np.asarray(acc)
+        a = (acc.detach().cpu().numpy() if hasattr(acc, "detach") else np.asarray(acc)).astype(np.float64)
         cnt = a[:, -1]
         nz = cnt > 0
         cen[nz] = (a[nz, :-1] / cnt[nz, None]).astype(np.float32)
@@ -38,7 +38,7 @@ def lloyd_split_gpu(ctx, X_shard: np.ndarray, centroids: np.ndarray, iters: int,
     import torch
     K, D = np.asarray(centroids).shape
     ctx.split_begin(X_shard, centroids)
-    acc = torch.empty((K, D + 1), dtype=torch.float32, device=torch.device("cuda", ctx.device))
+    acc = torch.empty((K, D + 1), dtype=torch.float64, device=torch.device("cuda", ctx.device))
     multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
     for _ in range(iters):
         ctx.split_step(acc.data_ptr())              # returns with the library stream idle

@@ -58,8 +58,8 @@ def _worker(rank, world, port, q):
 
         def partial(cen):      # stand-in for gsc_split_step: assign + per-cluster sums of this rank's points
             lab, _ = O.assign(feat[lo:hi], cen)
-            acc = np.zeros((128, 9), np.float32)
-            np.add.at(acc[:, :8], lab, feat[lo:hi])
+            acc = np.zeros((128, 9), np.float64)
+            np.add.at(acc[:, :8], lab, feat[lo:hi].astype(np.float64))
             acc[:, 8] = np.bincount(lab, minlength=128)
             return torch.from_numpy(acc)
 
@@ -99,3 +99,4 @@ def test_world_size_2_gloo():
     cref, _ = O.lloyd(feat, c0, 6)
     assert np.array_equal(cen0, cen1)
     assert np.max(np.abs(cen0 - cref) / np.maximum(np.abs(cref), 1e-6)) <= 1e-4
+    assert np.array_equal(cen0.view(np.uint32), cref.view(np.uint32))   # Double accumulation: order-independent

@@ -49,14 +49,18 @@ t = torch.tensor([dt], dtype=torch.float64, device="cuda")
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 out = {"config": "oversized frame split", "points": N, "K": a.K, "iters": a.iters, "n_gpus": world,
-       "seconds": float(t.item()), "allreduce_bytes_per_iter": a.K * 9 * 4,
+       "seconds": float(t.item()), "allreduce_bytes_per_iter": a.K * 9 * 8,
        "tflops_dense": 2.0 * N * a.K * 8 * (a.iters + 1) / float(t.item()) / 1e12}
 if a.check:
     ref_cen, ref_lab = ctx.lloyd(feat, c0, a.iters)
-    rel = float(np.max(np.abs(cen - ref_cen) / np.maximum(np.abs(ref_cen), 1e-6)))
-    out["max_rel_centroid_diff_vs_single_gpu"] = rel
+    # per centroid: largest coordinate difference relative to the centroid's largest coordinate
+    rel = np.max(np.abs(cen - ref_cen), axis=1) / np.maximum(np.max(np.abs(ref_cen), axis=1), 1e-12)
+    out["centroid_rel_diff"] = {"median": float(np.median(rel)), "p99": float(np.quantile(rel, 0.99)), "max": float(rel.max()),
+                                "frac_within_1e-4": float(np.mean(rel <= 1e-4))}
     out["label_mismatch_frac"] = float(np.mean(labels != ref_lab[lo:hi]))
-    assert rel <= 1e-4, rel
+    # Double accumulation makes the means independent of the summation order: expect identical results
+    out["bit_identical"] = bool(np.array_equal(cen.view(np.uint32), ref_cen.view(np.uint32)))
+    assert out["centroid_rel_diff"]["max"] <= 1e-4 and out["label_mismatch_frac"] == 0.0, out
 if rank == 0:
     print(json.dumps(out), flush=True)
 ctx.close()
