@@ -127,6 +127,48 @@ __device__ __forceinline__ float gsc_rate(int cnt) {  // enc:735
     return (float)(1.0 / sqrt((double)cnt));
 }
 
+// ---- packed FP32 pairs: one FFMA2 (fma.rn.f32x2, sm_100) does the filter FMA of two centroids ----
+__device__ __forceinline__ unsigned long long gsc_pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void gsc_upk2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long gsc_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+// s[2p], s[2p+1] = x . c + h for the thread's CPT centroids (DF = 4 filter dimensions)
+template <int CPT, int DF>
+__device__ __forceinline__ void gsc_filter_scores(const float (&x)[DF], const unsigned long long (&fcp)[CPT / 2][DF],
+                                                  const unsigned long long (&hp)[CPT / 2], float (&s)[CPT]) {
+    unsigned long long xx[DF], sp[CPT / 2];
+#pragma unroll
+    for (int k = 0; k < DF; ++k) xx[k] = gsc_pk2(x[k], x[k]);
+#pragma unroll
+    for (int p = 0; p < CPT / 2; ++p) sp[p] = hp[p];
+#pragma unroll
+    for (int k = 0; k < DF; ++k)
+#pragma unroll
+        for (int p = 0; p < CPT / 2; ++p) sp[p] = gsc_ffma2(xx[k], fcp[p][k], sp[p]);
+#pragma unroll
+    for (int p = 0; p < CPT / 2; ++p) gsc_upk2(sp[p], s[2 * p], s[2 * p + 1]);
+}
+// replace centroid j (compile-time) of the packed filter copy
+template <int CPT, int DF>
+__device__ __forceinline__ void gsc_filter_set(unsigned long long (&fcp)[CPT / 2][DF], unsigned long long (&hp)[CPT / 2], int j,
+                                               const float *r, float hv) {
+#pragma unroll
+    for (int p = 0; p < CPT / 2; ++p) {
+        if (j == 2 * p || j == 2 * p + 1) {
+#pragma unroll
+            for (int k = 0; k < DF; ++k) {
+                float lo, hi;
+                gsc_upk2(fcp[p][k], lo, hi);
+                fcp[p][k] = (j == 2 * p) ? gsc_pk2(r[k], hi) : gsc_pk2(lo, r[k]);
+            }
+            float lo, hi;
+            gsc_upk2(hp[p], lo, hi);
+            hp[p] = (j == 2 * p) ? gsc_pk2(hv, hi) : gsc_pk2(lo, hv);
+        }
+    }
+}
+
 // minimum of 64-bit keys over a warp (two 32-bit redux steps)
 __device__ __forceinline__ unsigned long long gsc_warp_min_key(unsigned long long k) {
     const unsigned kd = gsc_kd(k), ki = gsc_ki(k);
@@ -145,23 +187,21 @@ struct GscOnLayout {
     static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [B][L]
     static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B][W] entries per (point, warp) sub-list
     static constexpr unsigned THRW = LISTN + GSC_ON_B * (T / 32) * 4; // float [W][B] candidate thresholds (per-warp copy)
-    static constexpr unsigned OVER = THRW + GSC_ON_B * (T / 32) * 4;  // int   [B] a sub-list overflowed
-    static constexpr unsigned ABEST = OVER + GSC_ON_B * 4;            // u64   [B]
-    static constexpr unsigned MOVED = ABEST + GSC_ON_B * 8;           // int   [B]
+    static constexpr unsigned MOVED = THRW + GSC_ON_B * (T / 32) * 4; // int   [B]
     static constexpr unsigned ROWS = MOVED + GSC_ON_B * 4;            // float [B][D]
     static constexpr unsigned WS = ROWS + GSC_ON_B * D * 4;           // int   [B]
     static constexpr unsigned ETB = WS + GSC_ON_B * 4;                // float [2][B]
-    static constexpr unsigned WKEY = ETB + 2 * GSC_ON_B * 4;          // u64   [32]
-    static constexpr unsigned FK = WKEY + 32 * 8;                     // u64   [B(u)][B(lane)] fresh keys of a round
+    static constexpr unsigned WKEY = ETB + 2 * GSC_ON_B * 4;          // u64   [B][W] re-filter minima per (request, warp)
+    static constexpr unsigned FK = WKEY + GSC_ON_B * (T / 32) * 8;    // u64   [B(u)][B(lane)] fresh keys of a round
     static constexpr unsigned KEYS = FK + GSC_ON_B * GSC_ON_B * 8;    // u64   [B] proposals of a round
     static constexpr unsigned CB = KEYS + GSC_ON_B * 8;               // u32   [B] conflict ballots per row u
     static constexpr unsigned DIRTY = CB + GSC_ON_B * 4;              // u32   [T] moved centroids per owner thread
-    static constexpr unsigned T0 = DIRTY + T * 4;                     // int
-    static constexpr unsigned TMAX = T0 + 4;                          // int
-    static constexpr unsigned MODE = TMAX + 4;                        // int
-    static constexpr unsigned EPOINT = MODE + 4;                      // int
-    static constexpr unsigned ETHR = EPOINT + 4;                      // float
-    static constexpr unsigned STOP = ETHR + 4;                        // int
+    static constexpr unsigned EPTS = DIRTY + T * 4;                   // int   [B] points to re-filter
+    static constexpr unsigned ETHRS = EPTS + GSC_ON_B * 4;            // float [B] ... and their thresholds
+    static constexpr unsigned T0 = ETHRS + GSC_ON_B * 4;              // int
+    static constexpr unsigned NE = T0 + 4;                            // int
+    static constexpr unsigned MODE = NE + 4;                          // int
+    static constexpr unsigned STOP = MODE + 4;                        // int
     static constexpr unsigned ERR = ((STOP + 4 + 7) / 8) * 8;         // double
     static constexpr unsigned MFLAG = ((ERR + 8 + 15) / 16) * 16;     // u8    [KP]
     static constexpr unsigned RATE = ((MFLAG + KP + 15) / 16) * 16;   // float [KP]
@@ -202,7 +242,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     float *cf = cen + (long long)f.slot * Kmax * D;
 
     // codebook -> shared rows + register filter copy; dead slots (idx >= K) are NaN and never win
-    float fc[CPT][DF], h[CPT];
+    static_assert(CPT % 2 == 0 && DF == 4, "packed filter copy");
+    unsigned long long fcp[CPT / 2][DF], hp[CPT / 2];   // pairs of centroids: (2p, 2p+1)
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
         const int idx = first + j;
@@ -211,10 +252,10 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             r[k] = (idx < K) ? cf[(long long)idx * D + k] : __int_as_float(0x7fc00000);
-            if (k < DF) { fc[j][k] = r[k]; nc = fmaf(r[k], r[k], nc); }
+            if (k < DF) nc = fmaf(r[k], r[k], nc);
         }
         gsc_sts_row<D>(sb + Ly::C + (unsigned)idx * D * 4, r);
-        h[j] = -0.5f * nc * (1.0f - GSC_ON_G);
+        gsc_filter_set<CPT, DF>(fcp, hp, j, r, -0.5f * nc * (1.0f - GSC_ON_G));
     }
     for (int j = tid; j < 2 * KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
     for (int j = tid; j < KP / 4; j += T) gsc_sts_i(sb + Ly::MFLAG + 4u * j, 0);
@@ -272,8 +313,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
                                 float nc = 0.0f;
 #pragma unroll
-                                for (int k = 0; k < DF; ++k) { fc[j][k] = r[k]; nc = fmaf(r[k], r[k], nc); }
-                                h[j] = -0.5f * nc * (1.0f - GSC_ON_G);
+                                for (int k = 0; k < DF; ++k) nc = fmaf(r[k], r[k], nc);
+                                gsc_filter_set<CPT, DF>(fcp, hp, j, r, -0.5f * nc * (1.0f - GSC_ON_G));
                             }
                     }
                 }
@@ -303,12 +344,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const float4 t4 = gsc_lds_f4(sb + Ly::X + (unsigned)(pos + b) * D * 4);
                     const float xq[4] = {t4.x, t4.y, t4.z, t4.w};
                     float s[CPT];
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j) s[j] = h[j];
-#pragma unroll
-                    for (int k = 0; k < DF; ++k)
-#pragma unroll
-                        for (int j = 0; j < CPT; ++j) s[j] = fmaf(xq[k], fc[j][k], s[j]);
+                    gsc_filter_scores<CPT, DF>(xq, fcp, hp, s);
                     float smax = s[0];
 #pragma unroll
                     for (int j = 1; j < CPT; ++j) smax = fmaxf(smax, s[j]);   // NaN-safe: fmaxf ignores NaN
@@ -322,12 +358,10 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     float x[D];
                     gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b) * D * 4, x);
                     float s[CPT];
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j) s[j] = h[j];
-#pragma unroll
-                    for (int k = 0; k < DF; ++k)
-#pragma unroll
-                        for (int j = 0; j < CPT; ++j) s[j] = fmaf(x[k], fc[j][k], s[j]);
+                    {
+                        const float xq[DF] = {x[0], x[1], x[2], x[3]};
+                        gsc_filter_scores<CPT, DF>(xq, fcp, hp, s);
+                    }
                     unsigned m = 0;
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
@@ -346,54 +380,43 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                 }
                 if (tid == 0) { const unsigned long long t1 = clock64(); c_flt += t1 - c_tx; c_tx = t1; }
                 __syncthreads();   // ---- bar 1: candidate lists complete ----
-                if (tid == 0) { const unsigned long long t1 = clock64(); c_b1 += t1 - c_tx; c_tx = t1; }
-                // ============ phase 1.5: warp <-> point: close the sub-lists, best key of the point ============
-                {
-                    constexpr int PW = (B + W - 1) / W;   // points per warp
-#pragma unroll
-                    for (int i = 0; i < PW; ++i) {
-                        const int b = warp + i * W;
-                        if (b < nb) {   // uniform per warp
-                            const int cw = (lane < W) ? gsc_lds_i(sb + Ly::LISTN + (unsigned)(b * W + lane) * 4u) : 0;
-                            if (lane < W) gsc_sts_i(sb + Ly::LISTN + (unsigned)(b * W + lane) * 4u, 0);
-                            const unsigned ov = __ballot_sync(FULL, cw > SL);
-                            unsigned long long mk = GSC_KNONE;
-#pragma unroll
-                            for (int q = 0; q < L / 32; ++q) {
-                                const int slot = lane + 32 * q;
-                                const int cnt = __shfl_sync(FULL, cw, slot / SL);
-                                const unsigned sa = sb + Ly::LIST + (unsigned)(b * L + slot) * 8u;
-                                if ((slot % SL) < cnt) { const unsigned long long kk = gsc_lds_u64(sa); if (kk < mk) mk = kk; }
-                                else gsc_sts_u64(sa, GSC_KNONE);
-                            }
-                            mk = gsc_warp_min_key(mk);
-                            if (lane == 0) {
-                                gsc_sts_u64(sb + Ly::ABEST + 8u * b, mk);
-                                gsc_sts_i(sb + Ly::OVER + 4u * b, ov ? 1 : 0);
-                            }
-                            if (warp == 0) { int tot = cw; for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o); c_cands += tot; c_over += ov ? 1 : 0; }
-                        }
-                    }
-                }
-                if (tid == 0) { const unsigned long long t1 = clock64(); c_15 += t1 - c_tx; c_tx = t1; }
-                __syncthreads();   // ---- bar 2: keys complete ----
-                if (tid == 0) { const unsigned long long t1 = clock64(); c_ph1 += t1 - c_t0; c_t0 = t1; }
+                if (tid == 0) { const unsigned long long t1 = clock64(); c_b1 += t1 - c_tx; c_ph1 += t1 - c_t0; c_t0 = t1; }
                 // thread 32 adds the error terms of the previous batch while warp 0 opens this one
                 if (tid == 32 && prev_nb) {
                     const unsigned eb = sb + Ly::ETB + (unsigned)(((nbatch - 1) & 1) * B) * 4u;
                     for (int p = 0; p < prev_nb; ++p) e_run += (double)gsc_lds_f(eb + 4u * p);
                 }
                 // ============ phase 2: the batch is resolved in rounds ============
-                // warp 0 lane state
-                unsigned long long abest = GSC_KNONE, fresh = GSC_KNONE, key = GSC_KNONE, fkey = GSC_KNONE;
-                int over = 0, t0 = 0, nm = 0, tmax = 0, w = 0, pending = GSC_MODE_DONE, forced = 0;
-                bool act = false;
+                // warp 0 lane state: abest = best key among the list entries whose centroid has not moved
+                // (or, after a re-filter, among ALL unmoved centroids: `exact`), fresh = best key among the moved
+                unsigned long long abest = GSC_KNONE, fresh = GSC_KNONE, key = GSC_KNONE;
+                int over = 0, exact = 0, t0 = 0, nm = 0, w = 0, pending = GSC_MODE_DONE;
+                unsigned badmask = 0;
+                float dkreq = INFINITY;
                 float rn[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) rn[k] = 0.0f;
+                // best key of the lane's own candidate list, skipping moved centroids (all lanes of warp 0 may call)
+                auto scan_list = [&](bool skip_moved) -> unsigned long long {
+                    unsigned long long best = GSC_KNONE;
+                    int cw[W];
+#pragma unroll
+                    for (int ww = 0; ww < W; ++ww) cw[ww] = min(gsc_lds_i(sb + Ly::LISTN + (unsigned)(lane * W + ww) * 4u), SL);
+#pragma unroll
+                    for (int ww = 0; ww < W; ++ww)
+                        for (int e = 0; e < cw[ww]; ++e) {
+                            const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + ww * SL + e) * 8u);
+                            if (kk < best && !(skip_moved && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(kk)))) best = kk;
+                        }
+                    return best;
+                };
                 if (warp == 0 && lane < nb) {
-                    over = gsc_lds_i(sb + Ly::OVER + 4u * lane) | force_exact;
-                    abest = gsc_lds_u64(sb + Ly::ABEST + 8u * lane);
+                    int ovf = 0, tot = 0;
+#pragma unroll
+                    for (int ww = 0; ww < W; ++ww) { const int c0 = gsc_lds_i(sb + Ly::LISTN + (unsigned)(lane * W + ww) * 4u); ovf |= c0 > SL; tot += c0; }
+                    over = ovf | force_exact;
+                    abest = scan_list(false);
+                    c_cands += tot; c_over += ovf;
                 }
                 const unsigned etb = sb + Ly::ETB + (unsigned)((nbatch & 1) * B) * 4u;
                 for (;;) {
@@ -401,11 +424,11 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         if (pending == GSC_MODE_SCAN) {
                             // ---- R3: first conflicting lane, commit the lanes before it ----
                             unsigned firstc = 32u;
-                            if (lane >= t0 && lane < tmax) {
+                            if (lane >= t0 && lane < nb) {
                                 const unsigned cb = (unsigned)gsc_lds_i(sb + Ly::CB + 4u * lane);
                                 if (cb) firstc = (unsigned)(__ffs(cb) - 1);
                             }
-                            const int tstar = min(tmax, (int)__reduce_min_sync(FULL, firstc));
+                            const int tstar = min(nb, (int)__reduce_min_sync(FULL, firstc));
                             const bool commit = lane >= t0 && lane < tstar;
                             int already = 0;
                             if (commit) {
@@ -439,59 +462,59 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                     }
                                 }
                                 if (abest != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(abest))) {
-                                    // the list leader moved: best key among the entries that did not
-                                    abest = GSC_KNONE;
-                                    for (int e = 0; e < L; ++e) {
-                                        const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
-                                        if (kk < abest && !gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(kk))) abest = kk;
-                                    }
+                                    // the leader among the unmoved centroids moved
+                                    if (exact) { exact = 0; over = 1; abest = GSC_KNONE; }   // no list behind it: re-filter again
+                                    else abest = scan_list(true);
                                 }
                             }
                             t0 = tstar;
                         } else if (pending == GSC_MODE_REFILTER) {
-                            // exact best key of lane t0: re-filter minimum over the warps, or a moved centroid
-                            unsigned long long k2 = gsc_warp_min_key((lane < W) ? gsc_lds_u64(sb + Ly::WKEY + 8u * lane) : GSC_KNONE);
-                            const unsigned fd = __shfl_sync(FULL, gsc_kd(fresh), t0), fi = __shfl_sync(FULL, gsc_ki(fresh), t0);
-                            const unsigned long long f0 = gsc_pack(fd, fi);
-                            if (f0 < k2) k2 = f0;
-                            if (k2 == GSC_KNONE) k2 = gsc_pack(0x7f800000u, 0u);   // every row NaN: w = 0, d = +inf
-                            fkey = k2;
-                            forced = 1;
-                            ++c_exh;
+                            // ---- R3': every re-filtered lane now knows its exact best unmoved centroid ----
+                            if ((badmask >> lane) & 1u) {
+                                const int i = __popc(badmask & ((1u << lane) - 1u));
+                                unsigned long long k2 = GSC_KNONE;
+#pragma unroll
+                                for (int ww = 0; ww < W; ++ww) {
+                                    const unsigned long long kk = gsc_lds_u64(sb + Ly::WKEY + (unsigned)(i * W + ww) * 8u);
+                                    if (kk < k2) k2 = kk;
+                                }
+                                // k2 is the exact minimum over ALL unmoved centroids if one lies within the requested
+                                // distance dkreq; otherwise all that is known is "no unmoved centroid within dkreq"
+                                abest = k2; over = 0;
+                                exact = (k2 != GSC_KNONE) || !(dkreq < INFINITY);
+                                if (!exact) Umine = dkreq;
+                            }
+                            c_exh += __popc(badmask);
                         }
                         // ---- R1: proposals of the unresolved lanes ----
                         if (t0 >= nb) {
                             // hand over to the next batch
                             if (lane < nm) gsc_sts_u8(sb + Ly::MFLAG + (unsigned)gsc_lds_i(sb + Ly::MOVED + 4u * lane), 0);
+#pragma unroll
+                            for (int ww = 0; ww < W; ++ww) gsc_sts_i(sb + Ly::LISTN + (unsigned)(lane * W + ww) * 4u, 0);
                             if (lane == 0) gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
                             pending = GSC_MODE_DONE;
                             ++c_batches; c_points += nb;
                         } else {
-                            ++c_rounds;
-                            bool refilter = false;
-                            if (forced) {
-                                key = (lane == t0) ? fkey : GSC_KNONE;
-                                tmax = t0 + 1;
-                                forced = 0;
-                            } else {
-                                key = abest < fresh ? abest : fresh;
-                                const bool okl = !over && key != GSC_KNONE && __uint_as_float(gsc_kd(key)) <= Umine;
-                                const unsigned bad = __ballot_sync(FULL, lane >= t0 && lane < nb && !okl);
-                                tmax = bad ? (__ffs(bad) - 1) : nb;
-                                refilter = (tmax == t0);
-                            }
-                            if (refilter) {
-                                // lane t0 is not certified: re-filter it against its best known exact distance
-                                if (lane == t0) {
+                            key = abest < fresh ? abest : fresh;
+                            const bool okl = exact || (!over && key != GSC_KNONE && __uint_as_float(gsc_kd(key)) <= Umine);
+                            if (exact && key == GSC_KNONE) key = gsc_pack(0x7f800000u, 0u);   // every row NaN: w = 0, d = +inf
+                            badmask = __ballot_sync(FULL, lane >= t0 && lane < nb && !okl);
+                            if (badmask) {
+                                // uncertified lanes: re-filter each against its best known exact distance
+                                if ((badmask >> lane) & 1u) {
+                                    const int i = __popc(badmask & ((1u << lane) - 1u));
                                     const float dk = (key != GSC_KNONE && !force_exact) ? __uint_as_float(gsc_kd(key)) : INFINITY;
-                                    gsc_sts_i(sb + Ly::EPOINT, pos + t0);
-                                    gsc_sts_f(sb + Ly::ETHR, gsc_lds_f(sb + Ly::HX + 4u * (pos + t0)) - 0.5f * dk);
-                                    gsc_sts_i(sb + Ly::MODE, GSC_MODE_REFILTER);
+                                    dkreq = dk;
+                                    gsc_sts_i(sb + Ly::EPTS + 4u * i, pos + lane);
+                                    gsc_sts_f(sb + Ly::ETHRS + 4u * i, gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * dk);
                                 }
+                                if (lane == 0) { gsc_sts_i(sb + Ly::NE, __popc(badmask)); gsc_sts_i(sb + Ly::MODE, GSC_MODE_REFILTER); }
                                 pending = GSC_MODE_REFILTER;
                             } else {
-                                // speculative update of every proposing lane (enc:735-740)
-                                act = lane >= t0 && lane < tmax;
+                                ++c_rounds;
+                                // speculative update of every unresolved lane (enc:735-740)
+                                const bool act = lane >= t0 && lane < nb;
                                 w = act ? (int)gsc_ki(key) : 0;
                                 gsc_lds_row<D>(sb + Ly::C + (unsigned)w * D * 4, rn);
                                 const float rate = gsc_lds_f(sb + Ly::RATE + 4u * w);
@@ -500,59 +523,71 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 gsc_sts_row<D>(sb + Ly::ROWS + (unsigned)lane * D * 4, rn);
                                 gsc_sts_i(sb + Ly::WS + 4u * lane, act ? w : -1);
                                 gsc_sts_u64(sb + Ly::KEYS + 8u * lane, act ? key : GSC_KNONE);
-                                if (lane == 0) { gsc_sts_i(sb + Ly::T0, t0); gsc_sts_i(sb + Ly::TMAX, tmax); gsc_sts_i(sb + Ly::MODE, GSC_MODE_SCAN); }
+                                if (lane == 0) { gsc_sts_i(sb + Ly::T0, t0); gsc_sts_i(sb + Ly::MODE, GSC_MODE_SCAN); }
                                 pending = GSC_MODE_SCAN;
                             }
                         }
                     }
-                    __syncthreads();   // ---- bar 3: proposals / request visible ----
+                    __syncthreads();   // ---- bar 2: proposals / request visible ----
                     const int mode = gsc_lds_i(sb + Ly::MODE);
                     if (mode == GSC_MODE_DONE) break;
                     if (mode == GSC_MODE_SCAN) {
                         // ---- R2: lane t scores the proposed rows u (warp w takes u = t0+w, t0+w+W, ...) ----
-                        const int s0 = gsc_lds_i(sb + Ly::T0), s1 = gsc_lds_i(sb + Ly::TMAX);
+                        constexpr int UW = (B + W - 1) / W;
+                        const int s0 = gsc_lds_i(sb + Ly::T0);
                         const unsigned long long mykey = gsc_lds_u64(sb + Ly::KEYS + 8u * lane);
                         const int myw = gsc_lds_i(sb + Ly::WS + 4u * lane);
-                        for (int u = s0 + warp; u < s1; u += W) {
-                            const int wu = gsc_lds_i(sb + Ly::WS + 4u * u);
-                            float ru[D];
-                            gsc_lds_row<D>(sb + Ly::ROWS + (unsigned)u * D * 4, ru);
-                            const float d = gsc_ann_dist<D>(xb, ru);
-                            const unsigned long long kk = (d == d) ? gsc_pack(__float_as_uint(d), (unsigned)wu) : GSC_KNONE;
-                            gsc_sts_u64(sb + Ly::FK + (unsigned)(u * B + lane) * 8u, kk);
-                            const bool conf = (lane > u) && (lane < s1) && ((wu == myw) || (kk < mykey));
-                            const unsigned cb = __ballot_sync(FULL, conf);
-                            if (lane == 0) gsc_sts_i(sb + Ly::CB + 4u * u, (int)cb);
+                        int wu[UW];
+                        float ru[UW][D];
+#pragma unroll
+                        for (int i = 0; i < UW; ++i) {
+                            const int u = s0 + warp + i * W;
+                            wu[i] = -2;
+                            if (u < nb) { wu[i] = gsc_lds_i(sb + Ly::WS + 4u * u); gsc_lds_row<D>(sb + Ly::ROWS + (unsigned)u * D * 4, ru[i]); }
+                        }
+#pragma unroll
+                        for (int i = 0; i < UW; ++i) {
+                            const int u = s0 + warp + i * W;
+                            if (u < nb) {   // uniform per warp
+                                const float d = gsc_ann_dist<D>(xb, ru[i]);
+                                const unsigned long long kk = (d == d) ? gsc_pack(__float_as_uint(d), (unsigned)wu[i]) : GSC_KNONE;
+                                gsc_sts_u64(sb + Ly::FK + (unsigned)(u * B + lane) * 8u, kk);
+                                const bool conf = (lane > u) && (lane < nb) && ((wu[i] == myw) || (kk < mykey));
+                                const unsigned cb = __ballot_sync(FULL, conf);
+                                if (lane == 0) gsc_sts_i(sb + Ly::CB + 4u * u, (int)cb);
+                            }
                         }
                     } else {
-                        // ---- R2': re-filter ONE point with the whole CTA (exhaustive when the threshold is -inf) ----
-                        const int pe = gsc_lds_i(sb + Ly::EPOINT);
-                        const float thr = gsc_lds_f(sb + Ly::ETHR);
-                        float x[D];
-                        gsc_lds_row<D>(sb + Ly::X + (unsigned)pe * D * 4, x);
-                        float s[CPT];
+                        // ---- R2': re-filter the requested points with the whole CTA (threshold -inf = exhaustive) ----
+                        const int ne = gsc_lds_i(sb + Ly::NE);
+                        for (int i = 0; i < ne; ++i) {
+                            const int pe = gsc_lds_i(sb + Ly::EPTS + 4u * i);
+                            const float thr = gsc_lds_f(sb + Ly::ETHRS + 4u * i);
+                            float x[D];
+                            gsc_lds_row<D>(sb + Ly::X + (unsigned)pe * D * 4, x);
+                            float s[CPT];
+                            {
+                                const float xq[DF] = {x[0], x[1], x[2], x[3]};
+                                gsc_filter_scores<CPT, DF>(xq, fcp, hp, s);
+                            }
+                            unsigned m = 0;
 #pragma unroll
-                        for (int j = 0; j < CPT; ++j) s[j] = h[j];
-#pragma unroll
-                        for (int k = 0; k < DF; ++k)
-#pragma unroll
-                            for (int j = 0; j < CPT; ++j) s[j] = fmaf(x[k], fc[j][k], s[j]);
-                        unsigned m = 0;
-#pragma unroll
-                        for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
-                        unsigned long long best = GSC_KNONE;
-                        while (m) {
-                            const int j = __ffs(m) - 1;
-                            m &= m - 1;
-                            float r[D];
-                            gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
-                            const float d = gsc_ann_dist<D>(x, r);
-                            if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)(first + j)); if (kk < best) best = kk; }
+                            for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
+                            unsigned long long best = GSC_KNONE;
+                            while (m) {
+                                const int j = __ffs(m) - 1;
+                                m &= m - 1;
+                                if (gsc_lds_u8(sb + Ly::MFLAG + (unsigned)(first + j))) continue;   // moved: covered by the fresh keys
+                                float r[D];
+                                gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
+                                const float d = gsc_ann_dist<D>(x, r);
+                                if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)(first + j)); if (kk < best) best = kk; }
+                            }
+                            best = gsc_warp_min_key(best);
+                            if (lane == 0) gsc_sts_u64(sb + Ly::WKEY + (unsigned)(i * W + warp) * 8u, best);
                         }
-                        best = gsc_warp_min_key(best);
-                        if (lane == 0) gsc_sts_u64(sb + Ly::WKEY + 8u * warp, best);
                     }
-                    __syncthreads();   // ---- bar 4: round results complete ----
+                    __syncthreads();   // ---- bar 3: round results complete ----
                 }
                 if (tid == 0) c_ph2 += clock64() - c_t0;
                 prev_nb = nb;
