@@ -61,7 +61,7 @@
 
 #define GSC_ON_TP 256         // points per shared-memory tile
 #define GSC_ON_B 32           // points per batch (one per lane of the resolving warp)
-#define GSC_ON_L 64           // candidate list capacity per point (W sub-lists of L/W slots, one per warp)
+#define GSC_ON_L 32           // candidate list capacity per point
 #define GSC_ON_G 7.62939453125e-06f   // 2^-17
 #define GSC_NONE 0xffffffffu
 #define GSC_KNONE 0xffffffffffffffffull
@@ -185,8 +185,8 @@ struct GscOnLayout {
     static constexpr unsigned HX = X + GSC_ON_TP * D * 4;             // float [TP]
     static constexpr unsigned G = HX + GSC_ON_TP * 4;                 // int   [TP]
     static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [B][L]
-    static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B][W] entries per (point, warp) sub-list
-    static constexpr unsigned THRW = LISTN + GSC_ON_B * (T / 32) * 4; // float [W][B] candidate thresholds (per-warp copy)
+    static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B] entries per point (may exceed L: overflow)
+    static constexpr unsigned THRW = LISTN + GSC_ON_B * 4;            // float [W][B] candidate thresholds (per-warp copy)
     static constexpr unsigned MOVED = THRW + GSC_ON_B * (T / 32) * 4; // int   [B]
     static constexpr unsigned ROWS = MOVED + GSC_ON_B * 4;            // float [B][D]
     static constexpr unsigned WS = ROWS + GSC_ON_B * D * 4;           // int   [B]
@@ -226,8 +226,6 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     constexpr int W = T / 32;
     constexpr int KP = T * CPT;
     constexpr int B = GSC_ON_B, L = GSC_ON_L;
-    constexpr int SL = L / W;                  // slots per (point, warp) sub-list
-    static_assert(L % W == 0 && L % 32 == 0, "list geometry");
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smraw[];
     const unsigned sb = gsc_opaque(gsc_smem_u32(smraw));
@@ -260,14 +258,14 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     for (int j = tid; j < 2 * KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
     for (int j = tid; j < KP / 4; j += T) gsc_sts_i(sb + Ly::MFLAG + 4u * j, 0);
     gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
-    for (int j = tid; j < B * W; j += T) gsc_sts_i(sb + Ly::LISTN + 4u * j, 0);
+    if (tid < B) gsc_sts_i(sb + Ly::LISTN + 4u * tid, 0);
     if (tid == 0) {
         gsc_sts_d(sb + Ly::ERR, 3.40282346638528860e+38);
         gsc_sts_i(sb + Ly::STOP, 0); gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
     }
     __syncthreads();
 
-    unsigned long long c_ph1 = 0, c_ph2 = 0, c_t0 = 0, c_p0 = 0, c_flt = 0, c_b1 = 0, c_15 = 0, c_tx = 0;
+    unsigned long long c_ph1 = 0, c_ph2 = 0, c_t0 = 0, c_p0 = 0, c_flt = 0, c_b1 = 0, c_15 = 0, c_tx = 0, c_r3 = 0, c_r1 = 0, c_r2 = 0;
     unsigned long long c_batches = 0, c_exh = 0, c_rounds = 0, c_over = 0, c_points = 0, c_cands = 0;
     int iter = 0;
     for (;;) {
@@ -372,9 +370,9 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
                         const float d = gsc_ann_dist<D>(x, r);
                         if (d == d) {
-                            const int slot = gsc_atoms_add(sb + Ly::LISTN + (unsigned)(b * W + warp) * 4u, 1);
-                            if (slot < SL)
-                                gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + warp * SL + slot) * 8u, gsc_pack(__float_as_uint(d), (unsigned)(first + j)));
+                            const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)(first + j));
+                            const int slot = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);   // ~3 candidates per point: no contention
+                            if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + slot) * 8u, kk);
                         }
                     }
                 }
@@ -397,30 +395,27 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
 #pragma unroll
                 for (int k = 0; k < D; ++k) rn[k] = 0.0f;
                 // best key of the lane's own candidate list, skipping moved centroids (all lanes of warp 0 may call)
+                int nl = 0;
                 auto scan_list = [&](bool skip_moved) -> unsigned long long {
                     unsigned long long best = GSC_KNONE;
-                    int cw[W];
-#pragma unroll
-                    for (int ww = 0; ww < W; ++ww) cw[ww] = min(gsc_lds_i(sb + Ly::LISTN + (unsigned)(lane * W + ww) * 4u), SL);
-#pragma unroll
-                    for (int ww = 0; ww < W; ++ww)
-                        for (int e = 0; e < cw[ww]; ++e) {
-                            const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + ww * SL + e) * 8u);
-                            if (kk < best && !(skip_moved && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(kk)))) best = kk;
-                        }
+                    for (int e = 0; e < nl; ++e) {
+                        const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
+                        if (kk < best && !(skip_moved && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(kk)))) best = kk;
+                    }
                     return best;
                 };
                 if (warp == 0 && lane < nb) {
-                    int ovf = 0, tot = 0;
-#pragma unroll
-                    for (int ww = 0; ww < W; ++ww) { const int c0 = gsc_lds_i(sb + Ly::LISTN + (unsigned)(lane * W + ww) * 4u); ovf |= c0 > SL; tot += c0; }
-                    over = ovf | force_exact;
+                    nl = gsc_lds_i(sb + Ly::LISTN + 4u * lane);
+                    over = (nl > L) | force_exact;
+                    if (tid == 0) { c_cands += nl; c_over += nl > L; }
+                    nl = min(nl, L);
                     abest = scan_list(false);
-                    c_cands += tot; c_over += ovf;
                 }
                 const unsigned etb = sb + Ly::ETB + (unsigned)((nbatch & 1) * B) * 4u;
+                if (tid == 0) { const unsigned long long t1 = clock64(); c_15 += t1 - c_t0; c_tx = t1; }
                 for (;;) {
                     if (warp == 0) {
+                        if (tid == 0) c_tx = clock64();
                         if (pending == GSC_MODE_SCAN) {
                             // ---- R3: first conflicting lane, commit the lanes before it ----
                             unsigned firstc = 32u;
@@ -437,7 +432,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 lab[base + pos + lane] = w;                                               // enc:742
                                 gsc_sts_f(etb + 4u * lane, sqrtf(__uint_as_float(gsc_kd(key)) / (float)D));  // enc:743 (term)
                                 already = gsc_lds_u8(sb + Ly::MFLAG + (unsigned)w);
-                                gsc_sts_u8(sb + Ly::MFLAG + (unsigned)w, 1);
+                                gsc_sts_u8(sb + Ly::MFLAG + (unsigned)w, already ? 2 : 1);   // 2: moved again in this round
                                 gsc_sts_i(sb + Ly::MOVED + 4u * (nm + lane - t0), w);
                                 gsc_atoms_or(sb + Ly::DIRTY + 4u * (unsigned)(w / CPT), 1u << (w % CPT));
                             }
@@ -446,12 +441,17 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                             __syncwarp();
                             // unresolved lanes take over the fresh keys of the committed rows
                             if (lane >= tstar && lane < nb) {
-                                for (int u = t0; u < tstar; ++u) {
-                                    const unsigned long long kk = gsc_lds_u64(sb + Ly::FK + (unsigned)(u * B + lane) * 8u);
-                                    if (kk < fresh) fresh = kk;
+                                for (int u = t0; u < tstar; u += 4) {   // 4 independent loads per step
+                                    unsigned long long kq[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        kq[q] = (u + q < tstar) ? gsc_lds_u64(sb + Ly::FK + (unsigned)((u + q) * B + lane) * 8u) : GSC_KNONE;
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) if (kq[q] < fresh) fresh = kq[q];
                                 }
-                                if (anyal) {
-                                    // a centroid moved twice: older fresh keys may be stale, rebuild from the moved list
+                                if (anyal && fresh != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(fresh)) == 2) {
+                                    // this lane's best moved centroid moved again: its key is stale, rebuild from the moved list
+                                    // (the other lanes' minima are over centroids that did not move again and stay valid)
                                     fresh = GSC_KNONE;
                                     for (int m = 0; m < nm; ++m) {
                                         const int id = gsc_lds_i(sb + Ly::MOVED + 4u * m);
@@ -466,6 +466,10 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                     if (exact) { exact = 0; over = 1; abest = GSC_KNONE; }   // no list behind it: re-filter again
                                     else abest = scan_list(true);
                                 }
+                            }
+                            if (anyal) {
+                                __syncwarp();
+                                if (commit && already) gsc_sts_u8(sb + Ly::MFLAG + (unsigned)w, 1);
                             }
                             t0 = tstar;
                         } else if (pending == GSC_MODE_REFILTER) {
@@ -486,12 +490,12 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                             }
                             c_exh += __popc(badmask);
                         }
+                        if (tid == 0) { const unsigned long long t1 = clock64(); c_r3 += t1 - c_tx; c_tx = t1; }
                         // ---- R1: proposals of the unresolved lanes ----
                         if (t0 >= nb) {
                             // hand over to the next batch
                             if (lane < nm) gsc_sts_u8(sb + Ly::MFLAG + (unsigned)gsc_lds_i(sb + Ly::MOVED + 4u * lane), 0);
-#pragma unroll
-                            for (int ww = 0; ww < W; ++ww) gsc_sts_i(sb + Ly::LISTN + (unsigned)(lane * W + ww) * 4u, 0);
+                            gsc_sts_i(sb + Ly::LISTN + 4u * lane, 0);
                             if (lane == 0) gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
                             pending = GSC_MODE_DONE;
                             ++c_batches; c_points += nb;
@@ -528,6 +532,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                             }
                         }
                     }
+                    if (tid == 0) { const unsigned long long t1 = clock64(); c_r1 += t1 - c_tx; c_tx = t1; }
                     __syncthreads();   // ---- bar 2: proposals / request visible ----
                     const int mode = gsc_lds_i(sb + Ly::MODE);
                     if (mode == GSC_MODE_DONE) break;
@@ -588,6 +593,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         }
                     }
                     __syncthreads();   // ---- bar 3: round results complete ----
+                    if (tid == 0) { const unsigned long long t1 = clock64(); c_r2 += t1 - c_tx; c_tx = t1; }
                 }
                 if (tid == 0) c_ph2 += clock64() - c_t0;
                 prev_nb = nb;
@@ -626,7 +632,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         if (dbg) {
             unsigned long long *o = dbg + (long long)f.slot * 16;
             o[0] = c_batches; o[1] = c_points; o[2] = c_exh; o[3] = c_rounds; o[4] = c_over; o[5] = c_cands; o[6] = c_ph1; o[7] = c_ph2;
-            o[8] = c_p0; o[9] = c_flt; o[10] = c_b1; o[11] = c_15;
+            o[8] = c_p0; o[9] = c_flt; o[10] = c_b1; o[11] = c_15; o[12] = c_r3; o[13] = c_r1; o[14] = c_r2;
         }
     }
 }
