@@ -468,12 +468,7 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
         if (K <= 512) return online_launch<8, 8, 64>(c, tol, max_passes, fe);
         if (K <= 1024) return online_launch<8, 8, 128>(c, tol, max_passes, fe);
         if (K <= 2048) return online_launch<8, 16, 128>(c, tol, max_passes, fe);
-        if (K <= 4096) {
-            static int wide = -1;
-            if (wide < 0) { const char *e = getenv("GSC_ONLINE_T"); wide = (e && atoi(e) == 512) ? 1 : 0; }
-            if (wide) return online_launch<8, 8, 512>(c, tol, max_passes, fe);
-            return online_launch<8, 16, 256>(c, tol, max_passes, fe);
-        }
+        if (K <= 4096) return online_launch<8, 16, 256>(c, tol, max_passes, fe);
     } else if (D == 4) {
         if (K <= 256) return online_launch<4, 4, 64>(c, tol, max_passes, fe);
         if (K <= 512) return online_launch<4, 8, 64>(c, tol, max_passes, fe);

@@ -123,6 +123,11 @@ __device__ __forceinline__ unsigned long long gsc_pack(unsigned dbits, unsigned 
 }
 __device__ __forceinline__ unsigned gsc_kd(unsigned long long k) { return (unsigned)(k >> 32); }
 __device__ __forceinline__ unsigned gsc_ki(unsigned long long k) { return (unsigned)(k & 0xffffffffu); }
+// The low word of a key is (original centroid index << 16) | slot: ties in the distance are broken by the
+// ORIGINAL index (the reference's order), the slot (position in the kernel's c0-sorted codebook) addresses memory.
+__device__ __forceinline__ unsigned gsc_ks(unsigned long long k) { return (unsigned)(k & 0xffffu); }
+__device__ __forceinline__ int gsc_lds_u16(unsigned a) { unsigned v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return (int)v; }
+__device__ __forceinline__ void gsc_sts_u16(unsigned a, int v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ float gsc_rate(int cnt) {  // enc:735
     return (float)(1.0 / sqrt((double)cnt));
 }
@@ -187,7 +192,9 @@ struct GscOnLayout {
     static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [B][L]
     static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B] entries per point (may exceed L: overflow)
     static constexpr unsigned THRW = LISTN + GSC_ON_B * 4;            // float [W][B] candidate thresholds (per-warp copy)
-    static constexpr unsigned MOVED = THRW + GSC_ON_B * (T / 32) * 4; // int   [B]
+    static constexpr unsigned XLO = THRW + GSC_ON_B * (T / 32) * 4;   // float [W][B] slab x0 - r  (per-warp copy)
+    static constexpr unsigned XHI = XLO + GSC_ON_B * (T / 32) * 4;    // float [W][B] slab x0 + r
+    static constexpr unsigned MOVED = XHI + GSC_ON_B * (T / 32) * 4;  // int   [B]
     static constexpr unsigned ROWS = MOVED + GSC_ON_B * 4;            // float [B][D]
     static constexpr unsigned WS = ROWS + GSC_ON_B * D * 4;           // int   [B]
     static constexpr unsigned ETB = WS + GSC_ON_B * 4;                // float [2][B]
@@ -199,11 +206,13 @@ struct GscOnLayout {
     static constexpr unsigned EPTS = DIRTY + T * 4;                   // int   [B] points to re-filter
     static constexpr unsigned ETHRS = EPTS + GSC_ON_B * 4;            // float [B] ... and their thresholds
     static constexpr unsigned T0 = ETHRS + GSC_ON_B * 4;              // int
-    static constexpr unsigned NE = T0 + 4;                            // int
+    static constexpr unsigned SLOT0 = T0 + 4;                         // int   slot of original centroid 0
+    static constexpr unsigned NE = SLOT0 + 4;                         // int
     static constexpr unsigned MODE = NE + 4;                          // int
     static constexpr unsigned STOP = MODE + 4;                        // int
     static constexpr unsigned ERR = ((STOP + 4 + 7) / 8) * 8;         // double
-    static constexpr unsigned MFLAG = ((ERR + 8 + 15) / 16) * 16;     // u8    [KP]
+    static constexpr unsigned S2O = ((ERR + 8 + 15) / 16) * 16;       // u16   [KP] slot -> original centroid index
+    static constexpr unsigned MFLAG = ((S2O + 2 * KP + 15) / 16) * 16; // u8    [KP]
     static constexpr unsigned RATE = ((MFLAG + KP + 15) / 16) * 16;   // float [KP]
     static constexpr unsigned CNT = RATE + KP * 4;                    // int   [2][KP]
     static constexpr unsigned C = ((CNT + 2 * KP * 4 + 15) / 16) * 16;  // float [KP][D]
@@ -230,6 +239,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     extern __shared__ __align__(16) unsigned char smraw[];
     const unsigned sb = gsc_opaque(gsc_smem_u32(smraw));
 
+    // low word of a key for the centroid in `slot`
+    auto idword = [&](int slot) -> unsigned { return ((unsigned)gsc_lds_u16(sb + Ly::S2O + 2u * (unsigned)slot) << 16) | (unsigned)slot; };
     const GscFrame f = frames[blockIdx.x];
     const int K = f.K, N = f.N;
     if (K <= 0) return;
@@ -239,22 +250,66 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     int *lab = labels + f.chunk_off;
     float *cf = cen + (long long)f.slot * Kmax * D;
 
-    // codebook -> shared rows + register filter copy; dead slots (idx >= K) are NaN and never win
+    // ---- the kernel works on a c0-SORTED copy of the codebook (c0 = first feature): slot s holds the
+    // centroid with the s-th smallest c0 at the start, a warp owns a contiguous c0 range, and a point only
+    // visits the warps whose range meets [x0 - sqrt(U), x0 + sqrt(U)] (a centroid outside that slab has
+    // d >= (x0-c0)^2 > U).  Centroids drift during the passes; each thread keeps the exact [lo, hi] of its own
+    // c0 values, so the test stays valid, only its selectivity depends on the order.  Keys carry the original
+    // index for the reference's tie order.  Bitonic sort of (c0, index) in the CNT region (32 KB, not yet in use).
+    {
+        const unsigned sa = sb + Ly::CNT;
+        for (int i = tid; i < KP; i += T) {
+            unsigned kf = 0xffffffffu;
+            if (i < K) { const float c0 = cf[(long long)i * D]; kf = (c0 == c0) ? gsc_fkey(c0) : 0xfffffffeu; }
+            gsc_sts_u64(sa + 8u * i, ((unsigned long long)kf << 32) | (unsigned)i);
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= KP; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < KP; i += T) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long va = gsc_lds_u64(sa + 8u * i), vb = gsc_lds_u64(sa + 8u * l);
+                        if ((va > vb) == ((i & k2) == 0)) { gsc_sts_u64(sa + 8u * i, vb); gsc_sts_u64(sa + 8u * l, va); }
+                    }
+                }
+                __syncthreads();
+            }
+        // slot -> original (kept), original -> slot (temporary, in the FK region) for the incoming labels
+        for (int i = tid; i < KP; i += T) {
+            const int o = (int)(gsc_lds_u64(sa + 8u * i) & 0xffffu);
+            gsc_sts_u16(sb + Ly::S2O + 2u * i, o);
+            gsc_sts_u16(sb + Ly::FK + 2u * o, i);
+            if (o == 0) gsc_sts_i(sb + Ly::SLOT0, i);
+        }
+        __syncthreads();
+        for (int j = tid; j < N; j += T) {   // incoming guesses: original index -> slot
+            int gg = lab[j];
+            gg = (gg < 0 || gg >= K) ? 0 : gg;
+            lab[j] = gsc_lds_u16(sb + Ly::FK + 2u * gg);
+        }
+        __syncthreads();
+    }
+    // codebook -> shared rows + register filter copy; dead slots (original index >= K) are NaN and never win
     static_assert(CPT % 2 == 0 && DF == 4, "packed filter copy");
     unsigned long long fcp[CPT / 2][DF], hp[CPT / 2];   // pairs of centroids: (2p, 2p+1)
+    float c0lo = INFINITY, c0hi = -INFINITY;             // exact range of this thread's c0 values (NaN ignored)
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
         const int idx = first + j;
+        const int o = gsc_lds_u16(sb + Ly::S2O + 2u * idx);
         float r[D];
         float nc = 0.0f;
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            r[k] = (idx < K) ? cf[(long long)idx * D + k] : __int_as_float(0x7fc00000);
+            r[k] = (o < K) ? cf[(long long)o * D + k] : __int_as_float(0x7fc00000);
             if (k < DF) nc = fmaf(r[k], r[k], nc);
         }
         gsc_sts_row<D>(sb + Ly::C + (unsigned)idx * D * 4, r);
         gsc_filter_set<CPT, DF>(fcp, hp, j, r, -0.5f * nc * (1.0f - GSC_ON_G));
+        c0lo = fminf(c0lo, r[0]); c0hi = fmaxf(c0hi, r[0]);
     }
+    __syncthreads();   // the sort scratch (CNT) is free again
     for (int j = tid; j < 2 * KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
     for (int j = tid; j < KP / 4; j += T) gsc_sts_i(sb + Ly::MFLAG + 4u * j, 0);
     gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
@@ -285,7 +340,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
             for (int t = tid; t < tn * D; t += T) gsc_sts_f(sb + Ly::X + 4u * t, Xf[(long long)base * D + t]);
             for (int t = tid; t < tn; t += T) {
                 int gg = lab[base + t];
-                gsc_sts_i(sb + Ly::G + 4u * t, (gg < 0 || gg >= K) ? 0 : gg);
+                gsc_sts_i(sb + Ly::G + 4u * t, (gg < 0 || gg >= KP) ? 0 : gg);   // slot of the previous pass's centroid
             }
             __syncthreads();  // (B)
             for (int t = tid; t < tn; t += T) {
@@ -314,6 +369,13 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 for (int k = 0; k < DF; ++k) nc = fmaf(r[k], r[k], nc);
                                 gsc_filter_set<CPT, DF>(fcp, hp, j, r, -0.5f * nc * (1.0f - GSC_ON_G));
                             }
+                        c0lo = INFINITY; c0hi = -INFINITY;
+#pragma unroll
+                        for (int p2 = 0; p2 < CPT / 2; ++p2) {
+                            float a0, a1;
+                            gsc_upk2(fcp[p2][0], a0, a1);
+                            c0lo = fminf(c0lo, fminf(a0, a1)); c0hi = fmaxf(c0hi, fmaxf(a0, a1));
+                        }
                     }
                 }
                 if (tid == 0) { c_tx = clock64(); c_p0 += c_tx - c_t0; }
@@ -331,24 +393,25 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const float d = gsc_ann_dist<D>(xb, r);
                     Umine = (d == d) ? d * slack : INFINITY;   // any number is a valid threshold; see phase 2
                 }
-                // pass (a): branch-free filter over the 32 points -> one hit bit per (thread, point)
-                gsc_sts_f(sb + Ly::THRW + (unsigned)(warp * B + lane) * 4u,
-                          (lane < nb && !force_exact) ? gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * Umine : INFINITY);
-                __syncwarp();
-                unsigned hit = 0;
-#pragma unroll 4
-                for (int b = 0; b < B; ++b) {
-                    const float thr = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b) * 4u);   // candidate iff s >= thr (lb <= U)
-                    const float4 t4 = gsc_lds_f4(sb + Ly::X + (unsigned)(pos + b) * D * 4);
-                    const float xq[4] = {t4.x, t4.y, t4.z, t4.w};
-                    float s[CPT];
-                    gsc_filter_scores<CPT, DF>(xq, fcp, hp, s);
-                    float smax = s[0];
-#pragma unroll
-                    for (int j = 1; j < CPT; ++j) smax = fmaxf(smax, s[j]);   // NaN-safe: fmaxf ignores NaN
-                    hit |= (smax >= thr) ? (1u << b) : 0u;
+                {
+                    const bool on = lane < nb && !force_exact;
+                    // slab half-width: sqrt(U) widened for every rounding of the test and of the exact distance
+                    const float rr = sqrtf(Umine) * 1.000002f + 4.0e-7f * fabsf(xb[0]) + 1e-30f;
+                    gsc_sts_f(sb + Ly::THRW + (unsigned)(warp * B + lane) * 4u, on ? gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * Umine : INFINITY);
+                    gsc_sts_f(sb + Ly::XLO + (unsigned)(warp * B + lane) * 4u, on ? xb[0] - rr : INFINITY);
+                    gsc_sts_f(sb + Ly::XHI + (unsigned)(warp * B + lane) * 4u, on ? xb[0] + rr : -INFINITY);
                 }
-                // pass (b): expand the hits: which centroids, exact distance, key into the warp's sub-list
+                __syncwarp();
+                // pass (a): which points' slabs meet this thread's c0 range (one bit per point, branch-free)
+                unsigned hit = 0;
+#pragma unroll 8
+                for (int b = 0; b < B; ++b) {
+                    const float xl = gsc_lds_f(sb + Ly::XLO + (unsigned)(warp * B + b) * 4u);
+                    const float xh = gsc_lds_f(sb + Ly::XHI + (unsigned)(warp * B + b) * 4u);
+                    hit |= ((xh >= c0lo) && (xl <= c0hi)) ? (1u << b) : 0u;
+                }
+                // pass (b): for those points only: certified lower bounds of the thread's centroids (FFMA2 filter),
+                // exact distance of the survivors, key into the point's candidate list
                 while (hit) {
                     const int b = __ffs(hit) - 1;
                     hit &= hit - 1;
@@ -370,7 +433,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
                         const float d = gsc_ann_dist<D>(x, r);
                         if (d == d) {
-                            const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)(first + j));
+                            const unsigned long long kk = gsc_pack(__float_as_uint(d), idword(first + j));
                             const int slot = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);   // ~3 candidates per point: no contention
                             if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + slot) * 8u, kk);
                         }
@@ -400,7 +463,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     unsigned long long best = GSC_KNONE;
                     for (int e = 0; e < nl; ++e) {
                         const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
-                        if (kk < best && !(skip_moved && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(kk)))) best = kk;
+                        if (kk < best && !(skip_moved && gsc_lds_u8(sb + Ly::MFLAG + gsc_ks(kk)))) best = kk;
                     }
                     return best;
                 };
@@ -449,7 +512,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) if (kq[q] < fresh) fresh = kq[q];
                                 }
-                                if (anyal && fresh != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(fresh)) == 2) {
+                                if (anyal && fresh != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ks(fresh)) == 2) {
                                     // this lane's best moved centroid moved again: its key is stale, rebuild from the moved list
                                     // (the other lanes' minima are over centroids that did not move again and stay valid)
                                     fresh = GSC_KNONE;
@@ -458,10 +521,10 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                         float rm[D];
                                         gsc_lds_row<D>(sb + Ly::C + (unsigned)id * D * 4, rm);
                                         const float d = gsc_ann_dist<D>(xb, rm);
-                                        if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)id); if (kk < fresh) fresh = kk; }
+                                        if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), idword(id)); if (kk < fresh) fresh = kk; }
                                     }
                                 }
-                                if (abest != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ki(abest))) {
+                                if (abest != GSC_KNONE && gsc_lds_u8(sb + Ly::MFLAG + gsc_ks(abest))) {
                                     // the leader among the unmoved centroids moved
                                     if (exact) { exact = 0; over = 1; abest = GSC_KNONE; }   // no list behind it: re-filter again
                                     else abest = scan_list(true);
@@ -502,7 +565,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         } else {
                             key = abest < fresh ? abest : fresh;
                             const bool okl = exact || (!over && key != GSC_KNONE && __uint_as_float(gsc_kd(key)) <= Umine);
-                            if (exact && key == GSC_KNONE) key = gsc_pack(0x7f800000u, 0u);   // every row NaN: w = 0, d = +inf
+                            if (exact && key == GSC_KNONE) key = gsc_pack(0x7f800000u, idword(gsc_lds_i(sb + Ly::SLOT0)));   // every row NaN: centroid 0, d = +inf
                             badmask = __ballot_sync(FULL, lane >= t0 && lane < nb && !okl);
                             if (badmask) {
                                 // uncertified lanes: re-filter each against its best known exact distance
@@ -519,13 +582,13 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 ++c_rounds;
                                 // speculative update of every unresolved lane (enc:735-740)
                                 const bool act = lane >= t0 && lane < nb;
-                                w = act ? (int)gsc_ki(key) : 0;
+                                w = act ? (int)gsc_ks(key) : 0;
                                 gsc_lds_row<D>(sb + Ly::C + (unsigned)w * D * 4, rn);
                                 const float rate = gsc_lds_f(sb + Ly::RATE + 4u * w);
 #pragma unroll
                                 for (int k2 = 0; k2 < D; ++k2) { float v = xb[k2] - rn[k2]; float mm = v * rate; rn[k2] = rn[k2] + mm; }
                                 gsc_sts_row<D>(sb + Ly::ROWS + (unsigned)lane * D * 4, rn);
-                                gsc_sts_i(sb + Ly::WS + 4u * lane, act ? w : -1);
+                                gsc_sts_i(sb + Ly::WS + 4u * lane, act ? (int)gsc_ki(key) : -1);   // key low word (original << 16 | slot)
                                 gsc_sts_u64(sb + Ly::KEYS + 8u * lane, act ? key : GSC_KNONE);
                                 if (lane == 0) { gsc_sts_i(sb + Ly::T0, t0); gsc_sts_i(sb + Ly::MODE, GSC_MODE_SCAN); }
                                 pending = GSC_MODE_SCAN;
@@ -586,7 +649,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 float r[D];
                                 gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
                                 const float d = gsc_ann_dist<D>(x, r);
-                                if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), (unsigned)(first + j)); if (kk < best) best = kk; }
+                                if (d == d) { const unsigned long long kk = gsc_pack(__float_as_uint(d), idword(first + j)); if (kk < best) best = kk; }
                             }
                             best = gsc_warp_min_key(best);
                             if (lane == 0) gsc_sts_u64(sb + Ly::WKEY + (unsigned)(i * W + warp) * 8u, best);
@@ -616,15 +679,20 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         __syncthreads();
         if (gsc_lds_i(sb + Ly::STOP)) break;
     }
-    // the filter copies of the last batch's moved centroids are stale, the shared rows are the truth
+    // the shared rows are the truth; back to the caller's order: centroid rows and labels by original index
     for (int j = 0; j < CPT; ++j) {
         const int idx = first + j;
-        if (idx < K) {
+        const int o = gsc_lds_u16(sb + Ly::S2O + 2u * idx);
+        if (o < K) {
             float r[D];
             gsc_lds_row<D>(sb + Ly::C + (unsigned)idx * D * 4, r);
 #pragma unroll
-            for (int k = 0; k < D; ++k) cf[(long long)idx * D + k] = r[k];
+            for (int k = 0; k < D; ++k) cf[(long long)o * D + k] = r[k];
         }
+    }
+    for (int j = tid; j < N; j += T) {
+        const int sl = lab[j];
+        lab[j] = gsc_lds_u16(sb + Ly::S2O + 2u * (unsigned)((sl < 0 || sl >= KP) ? 0 : sl));
     }
     if (tid == 0) {
         passes_out[f.slot] = iter;
