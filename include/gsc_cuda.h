@@ -252,6 +252,9 @@ void gsc_debug_set_serial_scan(int on);
  * candidates (lane 0), phase-1 cycles, phase-2 cycles, then the phase-1 split:
  * refresh, filter, barrier wait, exact keys; rest reserved. */
 int gsc_debug_online_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
+/* Debug: cycles of the last seeding launch, 4 x uint64 per frame: seed pick,
+ * distance pass, prefix scan, number of steps. */
+int gsc_debug_seed_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
 
 /* FP32 FFMA throughput probe (roofline denominator for the k-means / search
  * kernels): returns measured TFLOP/s on the context's device. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
     "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters",
+    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters", "gsc_debug_seed_counters",
 ]
 
 
@@ -190,6 +190,11 @@ class Context:
     def online_counters(self, n_frames: int) -> np.ndarray:
         out = np.zeros((n_frames, 16), np.uint64)
         self._ck(self.L.gsc_debug_online_counters(C.c_void_p(self.h), _vp(out), n_frames))
+        return out
+
+    def seed_counters(self, n_frames: int) -> np.ndarray:
+        out = np.zeros((n_frames, 4), np.uint64)
+        self._ck(self.L.gsc_debug_seed_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
 
     def fp32_peak_tflops(self) -> float:

@@ -118,7 +118,7 @@ struct gsc_ctx {
     // device buffers
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
-        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg;
+        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg;
     HostBuf hpcm, hout;
     bool attr_set[4] = {false, false, false, false};
 };
@@ -181,7 +181,7 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
-                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg};
+                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg};
     for (DevBuf *b : bufs) b->release();
     c->hpcm.release();
     c->hout.release();
@@ -351,11 +351,13 @@ template <int D>
 static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
     size_t smem = (size_t)((c->maxN + 31) / 32) * 4;
     if (smem > 200 * 1024) return set_err(GSC_ERR_UNSUPPORTED, "frame too large for the seeding kernel");
+    TRY(c->sdbg.ensure(32 * (size_t)c->F));
+    CU(cudaMemsetAsync(c->sdbg.p, 0, 32 * (size_t)c->F, c->stream));
     SMEM_OPTIN(k_seed<D>, smem);
     LAUNCH(c, k_seed<D>, c->F, GSC_SEED_THREADS, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), init_type,
            c->pnorm.as<float>(), c->up.as<float>(), c->r.as<float>(), c->sid.as<int>(),
            want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax,
-           g_serial_scan);
+           g_serial_scan, c->sdbg.as<unsigned long long>());
     return GSC_OK;
 }
 
@@ -438,6 +440,14 @@ static int g_force_exact = -1;
 extern "C" void gsc_debug_set_online_exact(int on) { g_force_exact = on ? 1 : 0; }
 // Debug: counters of the last online k-means launch, 8 x uint64 per frame:
 // batches, points, exhaustive points, cuts (verification), cuts (list overflow), candidates.
+// Debug: cycles of the last seeding launch, 4 x uint64 per frame: pick, distance pass, prefix scan, steps.
+extern "C" int gsc_debug_seed_counters(gsc_ctx *c, unsigned long long *out, int n_frames) {
+    if (!c || !out || n_frames > c->F || !c->sdbg.p) return set_err(GSC_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out, c->sdbg.p, 32 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return GSC_OK;
+}
 extern "C" int gsc_debug_online_counters(gsc_ctx *c, unsigned long long *out, int n_frames) {
     if (!c || !out || n_frames > c->F || !c->dbg.p) return set_err(GSC_ERR_ARG, "bad arguments");
     CU(cudaSetDevice(c->device));

@@ -24,6 +24,9 @@ for K, bits in cfgs:
     print("K", K, "frames", nf, "wall", round(dt, 3), "audio-s/s", round(nf * 4.0 / dt, 1), "passes",
           [r.passes for r in res][:8], "R", [r.R for r in res][:4], "overfull", [r.overfull for r in res][:4])
     print({k: round(v, 2) for k, v in st["stage_ms"].items()})
+    sd = ctx.seed_counters(min(nf, 2)).astype(float)
+    for r in sd:
+        print(f"   seeding cycles/step: pick {r[0] / max(r[3], 1):.0f} distance {r[1] / max(r[3], 1):.0f} scan {r[2] / max(r[3], 1):.0f}")
     cn = ctx.online_counters(min(nf, 8)).astype(float)
     for r in cn[:4]:
         b, p, e, rd, ov, ca = r[:6]
