@@ -99,7 +99,7 @@ extern "C" void gsch_default_options(gsch_options *o) {
     o->lloyd_iters = 30;
     o->max_passes = 100;        // enc:703
     o->devices = 0;
-    o->frames_per_call = 296;
+    o->frames_per_call = 592;
 }
 
 extern "C" int gsch_parse_option(gsch_options *o, const char *a) {

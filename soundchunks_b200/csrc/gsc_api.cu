@@ -121,6 +121,11 @@ struct gsc_ctx {
         use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg;
     HostBuf hpcm, hout;
     bool attr_set[4] = {false, false, false, false};
+    // second lane: gsc_encode_frames splits a large batch over two streams so that the k-means tail of one
+    // half (few busy SMs) overlaps the seeding of the other
+    gsc_ctx *peer = nullptr;
+    bool split = false;
+    std::vector<int> idx_a, idx_b;   // frames of the last split batch handled by this context / by the peer
 };
 
 static std::atomic<int> g_rr{0};
@@ -175,6 +180,7 @@ extern "C" gsc_ctx *gsc_create(int device) {
 extern "C" void gsc_destroy(gsc_ctx *c) {
     if (!c) return;
     FpGuard g;
+    if (c->peer) { gsc_destroy(c->peer); c->peer = nullptr; }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->frames, &c->pcm, &c->divider, &c->vout, &c->attr, &c->atten, &c->feat, &c->dst,
@@ -197,16 +203,24 @@ extern "C" int gsc_synchronize(gsc_ctx *c) {
     FpGuard g;
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->peer) CU(cudaStreamSynchronize(c->peer->stream));
     return GSC_OK;
 }
 extern "C" int gsc_get_stats(gsc_ctx *c, gsc_stats *out) {
     if (!c || !out) return set_err(GSC_ERR_ARG, "null argument");
     *out = c->stats;
+    if (c->peer) {   // the second lane's work belongs to this context; its stage times are added (the lanes overlap)
+        out->kernel_launches += c->peer->stats.kernel_launches;
+        out->h2d_bytes += c->peer->stats.h2d_bytes;
+        out->d2h_bytes += c->peer->stats.d2h_bytes;
+        if (c->split) for (int i = 0; i < 8; ++i) out->last_stage_ms[i] += c->peer->stats.last_stage_ms[i];
+    }
     return GSC_OK;
 }
 extern "C" int gsc_reset_stats(gsc_ctx *c) {
     if (!c) return set_err(GSC_ERR_ARG, "null context");
     memset(&c->stats, 0, sizeof(c->stats));
+    if (c->peer) memset(&c->peer->stats, 0, sizeof(c->peer->stats));
     return GSC_OK;
 }
 
@@ -896,7 +910,7 @@ static int collect_stage_times(gsc_ctx *c) {
     return GSC_OK;
 }
 
-extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
+static int fetch_one(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
     FpGuard g;
     if (!c || !res || n_frames != c->F) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_results");
     CU(cudaSetDevice(c->device));
@@ -934,11 +948,8 @@ extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res
     return GSC_OK;
 }
 
-extern "C" int gsc_encode_frames(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P,
-                                 gsc_frame_result *results) {
-    FpGuard g;
-    if (!c || !frames || n_frames <= 0 || !results) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames");
-    TRY(check_params(P));
+// plan + stage + upload + enqueue the whole pipeline of one lane (host PCM); returns without waiting
+static int launch_host(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P) {
     CU(cudaSetDevice(c->device));
     TRY(plan_batch(c, frames, n_frames, P->chunk_size, P->chunks_per_frame, P->precision, true, nullptr));
     TRY(c->hpcm.ensure(2 * (size_t)c->pcm_samples));
@@ -951,16 +962,10 @@ extern "C" int gsc_encode_frames(gsc_ctx *c, const gsc_frame_desc *frames, int n
     TRY(c->pcm.ensure(2 * (size_t)c->pcm_samples));
     TRY(h2d(c, c->pcm.p, c->hpcm.p, 2 * (size_t)c->pcm_samples));
     TRY(upload_frames(c));
-    TRY(run_pipeline(c, P));
-    return gsc_fetch_results(c, n_frames, results);
+    return run_pipeline(c, P);
 }
 
-// Device-resident variant: frames[i].pcm are device pointers into one buffer
-// that the caller owns; the library reads it in place.
-extern "C" int gsc_encode_frames_dev(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P) {
-    FpGuard g;
-    if (!c || !frames || n_frames <= 0) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames_dev");
-    TRY(check_params(P));
+static int launch_dev(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P) {
     CU(cudaSetDevice(c->device));
     const int16_t *base = frames[0].pcm;
     for (int i = 1; i < n_frames; ++i) if (frames[i].pcm < base) base = frames[i].pcm;
@@ -973,6 +978,72 @@ extern "C" int gsc_encode_frames_dev(gsc_ctx *c, const gsc_frame_desc *frames, i
     int rc = run_pipeline(c, P);
     c->pcm = saved;
     return rc;
+}
+
+
+// ---- two lanes per context ---------------------------------------------------------------------
+static int lanes_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GSC_STREAMS"); v = (e && atoi(e) == 1) ? 0 : 1; }
+    return v;
+}
+#define GSC_SPLIT_MIN 16   // batches below this run on one stream
+
+// Decide the split of a batch (even / odd frames) and make sure the second lane exists.
+static int plan_lanes(gsc_ctx *c, int n_frames) {
+    c->split = lanes_enabled() && n_frames >= GSC_SPLIT_MIN;
+    c->idx_a.clear(); c->idx_b.clear();
+    if (!c->split) return GSC_OK;
+    if (!c->peer) {
+        c->peer = gsc_create(c->device);
+        if (!c->peer) return GSC_ERR_CUDA;
+    }
+    for (int i = 0; i < n_frames; ++i) ((i & 1) ? c->idx_b : c->idx_a).push_back(i);
+    return GSC_OK;
+}
+
+template <class Launch>
+static int launch_lanes(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P, Launch launch) {
+    TRY(plan_lanes(c, n_frames));
+    if (!c->split) return launch(c, frames, n_frames, P);
+    std::vector<gsc_frame_desc> fa, fb;
+    for (int i : c->idx_a) fa.push_back(frames[i]);
+    for (int i : c->idx_b) fb.push_back(frames[i]);
+    TRY(launch(c, fa.data(), (int)fa.size(), P));
+    return launch(c->peer, fb.data(), (int)fb.size(), P);
+}
+
+extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
+    FpGuard g;
+    if (!c || !res) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_results");
+    if (!c->split) return fetch_one(c, n_frames, res);
+    if (n_frames != (int)(c->idx_a.size() + c->idx_b.size())) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_results");
+    std::vector<gsc_frame_result> ra, rb;
+    for (int i : c->idx_a) ra.push_back(res[i]);
+    for (int i : c->idx_b) rb.push_back(res[i]);
+    TRY(fetch_one(c, (int)ra.size(), ra.data()));
+    TRY(fetch_one(c->peer, (int)rb.size(), rb.data()));
+    for (size_t k = 0; k < ra.size(); ++k) res[c->idx_a[k]] = ra[k];
+    for (size_t k = 0; k < rb.size(); ++k) res[c->idx_b[k]] = rb[k];
+    return GSC_OK;
+}
+
+extern "C" int gsc_encode_frames(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P,
+                                 gsc_frame_result *results) {
+    FpGuard g;
+    if (!c || !frames || n_frames <= 0 || !results) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames");
+    TRY(check_params(P));
+    TRY(launch_lanes(c, frames, n_frames, P, launch_host));
+    return gsc_fetch_results(c, n_frames, results);
+}
+
+// Device-resident variant: frames[i].pcm are device pointers into one buffer
+// that the caller owns; the library reads it in place.
+extern "C" int gsc_encode_frames_dev(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P) {
+    FpGuard g;
+    if (!c || !frames || n_frames <= 0) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames_dev");
+    TRY(check_params(P));
+    return launch_lanes(c, frames, n_frames, P, launch_dev);
 }
 
 extern "C" int gsc_fp32_peak_probe(gsc_ctx *c, double *tflops) {
