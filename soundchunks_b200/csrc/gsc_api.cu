@@ -8,6 +8,7 @@
 #include <xmmintrin.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -933,8 +934,12 @@ static int fetch_one(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
     TRY(d2h(c, h + o_attr, c->oattr.p, nN));
     TRY(d2h(c, h + o_dict, c->odict.p, 2 * fk * cs));
     TRY(d2h(c, h + o_datten, c->odatten.p, fk));
+    static const bool trace = getenv("GSC_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     TRY(sync(c));
+    const auto t1 = std::chrono::steady_clock::now();
     collect_stage_times(c);
+    if (trace) fprintf(stderr, "[gsc] fetch: wait for the stream %.3f s\n", std::chrono::duration<double>(t1 - t0).count());
     for (int i = 0; i < F; ++i) {
         const GscFrame &f = c->h_frames[i];
         gsc_frame_result &r = res[i];
@@ -945,6 +950,7 @@ static int fetch_one(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
         if (r.dict) memcpy(r.dict, h + o_dict + 2 * (size_t)i * Kmax * cs, 2 * (size_t)r.R * cs);
         if (r.datten) memcpy(r.datten, h + o_datten + (size_t)i * Kmax, (size_t)r.R);
     }
+    if (trace) fprintf(stderr, "[gsc] fetch: copy out %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
     return GSC_OK;
 }
 
@@ -1009,8 +1015,17 @@ static int launch_lanes(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, 
     std::vector<gsc_frame_desc> fa, fb;
     for (int i : c->idx_a) fa.push_back(frames[i]);
     for (int i : c->idx_b) fb.push_back(frames[i]);
+    // fork: the second lane starts after whatever the caller already queued on the context's stream (its PCM
+    // upload in the device-resident variant); join: the context's stream ends after both lanes, so an event the
+    // caller records on it covers the whole batch
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[8], c->stream));
+    CU(cudaStreamWaitEvent(c->peer->stream, c->ev[8], 0));
     TRY(launch(c, fa.data(), (int)fa.size(), P));
-    return launch(c->peer, fb.data(), (int)fb.size(), P);
+    TRY(launch(c->peer, fb.data(), (int)fb.size(), P));
+    CU(cudaEventRecord(c->peer->ev[8], c->peer->stream));
+    CU(cudaStreamWaitEvent(c->stream, c->peer->ev[8], 0));
+    return GSC_OK;
 }
 
 extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
@@ -1033,8 +1048,17 @@ extern "C" int gsc_encode_frames(gsc_ctx *c, const gsc_frame_desc *frames, int n
     FpGuard g;
     if (!c || !frames || n_frames <= 0 || !results) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames");
     TRY(check_params(P));
+    static const bool trace = getenv("GSC_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     TRY(launch_lanes(c, frames, n_frames, P, launch_host));
-    return gsc_fetch_results(c, n_frames, results);
+    const auto t1 = std::chrono::steady_clock::now();
+    int rc = gsc_fetch_results(c, n_frames, results);
+    if (trace) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gsc] encode_frames: launch %.3f s, fetch (incl. wait) %.3f s\n",
+                std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
+    }
+    return rc;
 }
 
 // Device-resident variant: frames[i].pcm are device pointers into one buffer
