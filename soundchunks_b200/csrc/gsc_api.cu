@@ -396,8 +396,8 @@ static int stage_seed(gsc_ctx *c, int D, int init_type, bool want_seeds) {
 static int stage_assign(gsc_ctx *c, int D, bool want_dist) {
     TRY(c->labels.ensure(4 * (size_t)c->sumN));
     if (want_dist) TRY(c->dist.ensure(4 * (size_t)c->sumN));
-    dim3 grid((c->maxN + 128 * GSC_ASSIGN_P - 1) / (128 * GSC_ASSIGN_P), c->F);
-    DISPATCH_D(D, LAUNCH(c, k_assign<D>, grid, 128, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
+    dim3 grid((c->maxN + GSC_ASSIGN_T * GSC_ASSIGN_P - 1) / (GSC_ASSIGN_T * GSC_ASSIGN_P), c->F);
+    DISPATCH_D(D, LAUNCH(c, k_assign<D>, grid, GSC_ASSIGN_T, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
                          c->labels.as<int>(), want_dist ? c->dist.as<float>() : nullptr, c->Kmax));
     return GSC_OK;
 }

@@ -1020,35 +1020,47 @@ __global__ void __launch_bounds__(256) k_finalize(const GscFrame *__restrict__ f
 
 // ---------------------------------------------------------------------------
 // Lloyd assign: exact nearest centroid (ANN distance, lowest index on ties).
-// Register tile of P points per thread; the codebook streams through shared
-// memory in tiles of 256 centroids.  A cheap FFMA lower bound
+// A cheap certified lower bound
 //   lb = (|c|^2)(1-g) - 2 x.c + (|x|^2)(1-g)   <=  d_exact
 // filters candidates; only rows with lb <= best are evaluated in the exact
 // operation order, so the result is the exact argmin.
 // grid = (ceil(maxN/(128*P)), F), block 128.
 // ---------------------------------------------------------------------------
 #define GSC_LB_GAMMA 7.62939453125e-06f  // 2^-17, covers every rounding of both forms
-#define GSC_ASSIGN_P 4
-#define GSC_ASSIGN_TILE 256
+#define GSC_ASSIGN_P 8            // points per thread (4 FFMA2 pairs)
+#define GSC_ASSIGN_T 128          // threads per CTA
+#define GSC_ASSIGN_TILE 256       // centroids per shared-memory tile
 
+__device__ __forceinline__ unsigned long long gsc_a_pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void gsc_a_upk2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long gsc_a_ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+
+// Register tile: 8 points per thread held as 4 packed pairs, so one FFMA2 (fma.rn.f32x2) advances the
+// lower-bound score of two points; the codebook tile is read from shared memory with broadcast loads
+// (2 x LDS.128 + 1 x LDS.32 per centroid for 64 FMAs).  Per (point, centroid): 8 FMAs + 1 compare; the exact
+// ANN-order distance is evaluated only for centroids whose certified lower bound does not exceed the point's
+// current best, so the result is the exact argmin (lowest index on ties).
 template <int D>
-__global__ void __launch_bounds__(128) k_assign(const GscFrame *__restrict__ frames,
-                                                const float *__restrict__ X,
-                                                const float *__restrict__ cen,  // [F][Kmax][D]
-                                                int *__restrict__ labels, float *__restrict__ dist,
-                                                int Kmax) {
-    __shared__ float s_c[GSC_ASSIGN_TILE * D];
+__global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restrict__ frames,
+                                                         const float *__restrict__ X,
+                                                         const float *__restrict__ cen,  // [F][Kmax][D]
+                                                         int *__restrict__ labels, float *__restrict__ dist,
+                                                         int Kmax) {
+    constexpr int P = GSC_ASSIGN_P, PP = P / 2;
+    __shared__ __align__(16) float s_c[GSC_ASSIGN_TILE * D];
     __shared__ float s_h[GSC_ASSIGN_TILE];  // -0.5*|c|^2*(1-g), NaN-safe
     const GscFrame f = frames[blockIdx.y];
     const int K = f.K;
-    const long long base = (long long)blockIdx.x * blockDim.x * GSC_ASSIGN_P;
+    const long long base = (long long)blockIdx.x * blockDim.x * P;
     if (base >= f.N) return;
     const float *Xf = X + f.chunk_off * D;
     const float *cf = cen + (long long)f.slot * Kmax * D;
-    float x[GSC_ASSIGN_P][D], thr[GSC_ASSIGN_P], bd[GSC_ASSIGN_P], hx[GSC_ASSIGN_P];
-    int bi[GSC_ASSIGN_P];
+    float x[P][D], thr[P], bd[P], hx[P];
+    int bi[P];
 #pragma unroll
-    for (int p = 0; p < GSC_ASSIGN_P; ++p) {
+    for (int p = 0; p < P; ++p) {
         const long long j = base + (long long)p * blockDim.x + threadIdx.x;
         if (j < f.N) gsc_load_row<D>(Xf, j, x[p]);
         else {
@@ -1062,6 +1074,11 @@ __global__ void __launch_bounds__(128) k_assign(const GscFrame *__restrict__ fra
         bd[p] = INFINITY; bi[p] = 0;
         thr[p] = -INFINITY;  // candidate iff s >= thr  (s = x.c - 0.5|c|^2(1-g))
     }
+    unsigned long long xp[PP][D];   // (x[2q][k], x[2q+1][k])
+#pragma unroll
+    for (int q = 0; q < PP; ++q)
+#pragma unroll
+        for (int k = 0; k < D; ++k) xp[q][k] = gsc_a_pk2(x[2 * q][k], x[2 * q + 1][k]);
     for (int k0 = 0; k0 < K; k0 += GSC_ASSIGN_TILE) {
         const int kt = min(GSC_ASSIGN_TILE, K - k0);
         __syncthreads();
@@ -1074,26 +1091,40 @@ __global__ void __launch_bounds__(128) k_assign(const GscFrame *__restrict__ fra
             s_h[t] = -0.5f * nc * (1.0f - GSC_LB_GAMMA);
         }
         __syncthreads();
+#pragma unroll 2
         for (int c = 0; c < kt; ++c) {
             float cc[D];
+            if (D % 4 == 0) {
 #pragma unroll
-            for (int k = 0; k < D; ++k) cc[k] = s_c[c * D + k];
-            const float h = s_h[c];
-            bool any = false;
-            float s[GSC_ASSIGN_P];
+                for (int k = 0; k < D / 4; ++k) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(&s_c[c * D + 4 * k]);
+                    cc[4 * k] = t4.x; cc[4 * k + 1] = t4.y; cc[4 * k + 2] = t4.z; cc[4 * k + 3] = t4.w;
+                }
+            } else {
 #pragma unroll
-            for (int p = 0; p < GSC_ASSIGN_P; ++p) {
-                float a = h;
-#pragma unroll
-                for (int k = 0; k < D; ++k) a = fmaf(x[p][k], cc[k], a);
-                s[p] = a;
-                any |= (a >= thr[p]);
+                for (int k = 0; k < D; ++k) cc[k] = s_c[c * D + k];
             }
+            const float h = s_h[c];
+            unsigned long long s2[PP];
+#pragma unroll
+            for (int q = 0; q < PP; ++q) s2[q] = gsc_a_pk2(h, h);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const unsigned long long ck = gsc_a_pk2(cc[k], cc[k]);
+#pragma unroll
+                for (int q = 0; q < PP; ++q) s2[q] = gsc_a_ffma2(xp[q][k], ck, s2[q]);
+            }
+            float sv[P];
+#pragma unroll
+            for (int q = 0; q < PP; ++q) gsc_a_upk2(s2[q], sv[2 * q], sv[2 * q + 1]);
+            bool any = false;
+#pragma unroll
+            for (int p = 0; p < P; ++p) any |= (sv[p] >= thr[p]);
             if (any) {
 #pragma unroll
-                for (int p = 0; p < GSC_ASSIGN_P; ++p)
-                    if (s[p] >= thr[p]) {
-                        float d = gsc_ann_dist<D>(x[p], cc);
+                for (int p = 0; p < P; ++p)
+                    if (sv[p] >= thr[p]) {
+                        const float d = gsc_ann_dist<D>(x[p], cc);
                         if (d < bd[p]) {
                             bd[p] = d; bi[p] = k0 + c;
                             // lb <= d  <=>  hx - s <= d/2  <=>  s >= hx - d/2
@@ -1104,7 +1135,7 @@ __global__ void __launch_bounds__(128) k_assign(const GscFrame *__restrict__ fra
         }
     }
 #pragma unroll
-    for (int p = 0; p < GSC_ASSIGN_P; ++p) {
+    for (int p = 0; p < P; ++p) {
         const long long j = base + (long long)p * blockDim.x + threadIdx.x;
         if (j < f.N) {
             labels[f.chunk_off + j] = bi[p];
