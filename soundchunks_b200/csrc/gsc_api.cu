@@ -404,9 +404,18 @@ static int stage_assign(gsc_ctx *c, int D, bool want_dist) {
 
 // Lloyd update into `acc` (Double [F][Kmax][D+1]; default: the context's own buffer), then means.
 static int stage_lloyd_sums(gsc_ctx *c, int D, double *acc) {
-    dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
-    DISPATCH_D(D, LAUNCH(c, k_owner_sums_d<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
-                         c->labels.as<int>(), acc, c->Kmax));
+    static int owner = -1;   // GSC_LLOYD_OWNER=1: per-cluster owner threads (ordered sums) instead of the scatter
+    if (owner < 0) { const char *e = getenv("GSC_LLOYD_OWNER"); owner = (e && e[0] == '1') ? 1 : 0; }
+    if (owner) {
+        dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
+        DISPATCH_D(D, LAUNCH(c, k_owner_sums_d<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
+                             c->labels.as<int>(), acc, c->Kmax));
+        return GSC_OK;
+    }
+    CU(cudaMemsetAsync(acc, 0, 8 * (size_t)c->F * c->Kmax * (D + 1), c->stream));
+    dim3 g((c->maxN + 255) / 256, c->F);
+    DISPATCH_D(D, LAUNCH(c, k_scatter_sums_d<D>, g, 256, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->labels.as<int>(),
+                         acc, c->Kmax));
     return GSC_OK;
 }
 static int stage_lloyd_means(gsc_ctx *c, int D, const double *acc) {

@@ -697,6 +697,28 @@ __global__ void __launch_bounds__(GSC_OWNER_THREADS) k_owner_sums_d(const GscFra
         o[D] = (double)cnt;
     }
 }
+// Same sums by scatter: one thread per point adds its row to its cluster's Double accumulators with
+// red.global.add.f64 (acc zeroed beforehand).  The order of the additions is arbitrary, which is exactly what
+// the Double accumulation + single rounding to Single makes harmless; ~21 points per cluster, little contention.
+template <int D>
+__global__ void __launch_bounds__(256) k_scatter_sums_d(const GscFrame *__restrict__ frames,
+                                                        const float *__restrict__ X,
+                                                        const int *__restrict__ labels,
+                                                        double *__restrict__ acc,   // [F][Kmax][D+1], zeroed
+                                                        int Kmax) {
+    const GscFrame f = frames[blockIdx.y];
+    if (f.K <= 0) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= f.N) return;
+    float p[D];
+    gsc_load_row<D>(X + f.chunk_off * D, j, p);
+    const int c = labels[f.chunk_off + j];
+    double *o = acc + ((long long)f.slot * Kmax + c) * (D + 1);
+#pragma unroll
+    for (int k = 0; k < D; ++k) atomicAdd(o + k, (double)p[k]);
+    atomicAdd(o + D, 1.0);
+}
+
 // centroid = Single(sum / count); empty clusters keep theirs.  acc may be the all-reduced buffer.
 template <int D>
 __global__ void k_means_from_acc(const GscFrame *__restrict__ frames, const double *__restrict__ acc,
@@ -1029,7 +1051,7 @@ __global__ void __launch_bounds__(256) k_finalize(const GscFrame *__restrict__ f
 #define GSC_LB_GAMMA 7.62939453125e-06f  // 2^-17, covers every rounding of both forms
 #define GSC_ASSIGN_P 8            // points per thread (4 FFMA2 pairs)
 #define GSC_ASSIGN_T 128          // threads per CTA
-#define GSC_ASSIGN_TILE 256       // centroids per shared-memory tile
+#define GSC_ASSIGN_TILE 512       // centroids per shared-memory tile
 
 __device__ __forceinline__ unsigned long long gsc_a_pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void gsc_a_upk2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -1049,6 +1071,9 @@ __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restr
                                                          int *__restrict__ labels, float *__restrict__ dist,
                                                          int Kmax) {
     constexpr int P = GSC_ASSIGN_P, PP = P / 2;
+    // dimensions of the bound: the second half of a feature row is the 1e-5-scaled cepstrum (enc:362); dropping
+    // those non-negative terms keeps lb <= d and halves the FMA work
+    constexpr int DF = (D >= 8) ? D / 2 : D;
     __shared__ __align__(16) float s_c[GSC_ASSIGN_TILE * D];
     __shared__ float s_h[GSC_ASSIGN_TILE];  // -0.5*|c|^2*(1-g), NaN-safe
     const GscFrame f = frames[blockIdx.y];
@@ -1069,16 +1094,16 @@ __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restr
         }
         float nx = 0.0f;
 #pragma unroll
-        for (int k = 0; k < D; ++k) nx = fmaf(x[p][k], x[p][k], nx);
+        for (int k = 0; k < DF; ++k) nx = fmaf(x[p][k], x[p][k], nx);
         hx[p] = 0.5f * nx * (1.0f - GSC_LB_GAMMA) - 1e-30f;
         bd[p] = INFINITY; bi[p] = 0;
         thr[p] = -INFINITY;  // candidate iff s >= thr  (s = x.c - 0.5|c|^2(1-g))
     }
-    unsigned long long xp[PP][D];   // (x[2q][k], x[2q+1][k])
+    unsigned long long xp[PP][DF];   // (x[2q][k], x[2q+1][k])
 #pragma unroll
     for (int q = 0; q < PP; ++q)
 #pragma unroll
-        for (int k = 0; k < D; ++k) xp[q][k] = gsc_a_pk2(x[2 * q][k], x[2 * q + 1][k]);
+        for (int k = 0; k < DF; ++k) xp[q][k] = gsc_a_pk2(x[2 * q][k], x[2 * q + 1][k]);
     for (int k0 = 0; k0 < K; k0 += GSC_ASSIGN_TILE) {
         const int kt = min(GSC_ASSIGN_TILE, K - k0);
         __syncthreads();
@@ -1087,29 +1112,29 @@ __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restr
         for (int t = threadIdx.x; t < kt; t += blockDim.x) {
             float nc = 0.0f;
 #pragma unroll
-            for (int k = 0; k < D; ++k) nc = fmaf(s_c[t * D + k], s_c[t * D + k], nc);
+            for (int k = 0; k < DF; ++k) nc = fmaf(s_c[t * D + k], s_c[t * D + k], nc);
             s_h[t] = -0.5f * nc * (1.0f - GSC_LB_GAMMA);
         }
         __syncthreads();
 #pragma unroll 2
         for (int c = 0; c < kt; ++c) {
-            float cc[D];
-            if (D % 4 == 0) {
+            float cc[DF];
+            if (DF % 4 == 0) {
 #pragma unroll
-                for (int k = 0; k < D / 4; ++k) {
+                for (int k = 0; k < DF / 4; ++k) {
                     const float4 t4 = *reinterpret_cast<const float4 *>(&s_c[c * D + 4 * k]);
                     cc[4 * k] = t4.x; cc[4 * k + 1] = t4.y; cc[4 * k + 2] = t4.z; cc[4 * k + 3] = t4.w;
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < D; ++k) cc[k] = s_c[c * D + k];
+                for (int k = 0; k < DF; ++k) cc[k] = s_c[c * D + k];
             }
             const float h = s_h[c];
             unsigned long long s2[PP];
 #pragma unroll
             for (int q = 0; q < PP; ++q) s2[q] = gsc_a_pk2(h, h);
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
+            for (int k = 0; k < DF; ++k) {
                 const unsigned long long ck = gsc_a_pk2(cc[k], cc[k]);
 #pragma unroll
                 for (int q = 0; q < PP; ++q) s2[q] = gsc_a_ffma2(xp[q][k], ck, s2[q]);
@@ -1124,7 +1149,10 @@ __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restr
 #pragma unroll
                 for (int p = 0; p < P; ++p)
                     if (sv[p] >= thr[p]) {
-                        const float d = gsc_ann_dist<D>(x[p], cc);
+                        float cr[D];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) cr[k] = s_c[c * D + k];
+                        const float d = gsc_ann_dist<D>(x[p], cr);
                         if (d < bd[p]) {
                             bd[p] = d; bi[p] = k0 + c;
                             // lb <= d  <=>  hx - s <= d/2  <=>  s >= hx - d/2
