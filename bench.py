@@ -60,6 +60,7 @@ def parse_args():
                     help="length of each frame of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lloyd", action="store_true", help="skip the secondary Lloyd-mode leg")
     return ap.parse_args()
 
 
@@ -296,7 +297,7 @@ def main():
     # the library runs a batch on two streams (even / odd frames); stage_ms are the CUDA-event stage times of both
     # lanes ADDED UP.  The lanes overlap, so the k-means kernels are busy for at most km_ms / 2 of wall time when both
     # lanes run side by side: the roofline uses km_ms / 2 ... km_ms; the conservative (full sum) figure is reported.
-    km_ms = stage_acc["kmeans"]
+    km_ms = ctx.stage_busy_ms("kmeans")     # wall time with a k-means kernel running on either stream (union)
     achieved = flops / (km_ms * 1e-3) / 1e12 if km_ms > 0 else 0.0
     roofline = {
         "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -326,6 +327,32 @@ def main():
                "ms_per_step": 1e3 * dt / args.steps, "api": "gsc_encode_frames (host buffers)"}
         assert [r.passes for r in r2] == passes, "host-buffer and device-resident legs disagree"
 
+    # secondary leg: the batch-Lloyd substitution (kmeans_mode = 1, BASELINE.json's register-tiled distance+argmin
+    # kernel) on the same frames, one step, to report the roofline of k_assign next to the default mode
+    lloyd = None
+    if args.mode == "online" and not args.no_lloyd:
+        lp = sc.default_params(chunk_bit_depth=args.bits, chunks_per_frame=args.chunks_per_frame, kmeans_mode=1,
+                               lloyd_iters=args.lloyd_iters)
+        ctx.encode_frames_dev(dev.data_ptr(), layout, lp)       # warm-up
+        ctx.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        ctx.encode_frames_dev(dev.data_ptr(), layout, lp)
+        l1.record(stream)
+        ctx.synchronize()
+        lres = ctx.fetch_results(layout, lp)
+        lst = ctx.stats()["stage_ms"]
+        lflops = sum(2.0 * r.N * K * D * (args.lloyd_iters + 1) for r in lres)
+        lms = l0.elapsed_time(l1)
+        lkm = ctx.stage_busy_ms("kmeans")
+        lloyd = {"value": audio_s_rank / (lms * 1e-3), "unit": UNIT + " (this rank)", "lloyd_iters": args.lloyd_iters,
+                 "ms_per_step": lms, "kmeans_stage_ms_sum_of_streams": lst["kmeans"], "kmeans_stage_busy_ms": lkm,
+                 "roofline": {"bound": "fp32", "kernel": "k_assign + k_scatter_sums_d", "unit": "TFLOP/s",
+                              "achieved": lflops / (lkm * 1e-3) / 1e12, "peak": fp32_peak,
+                              "frac": lflops / (lkm * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+                              "note": "dense count 2*N*K*D*(iters+1) / wall time with the stage running on either stream; "
+                                      "other stages of the other stream share the GPU during that time"}}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -342,7 +369,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, F, FRAME_SECONDS),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "lloyd_mode": lloyd,
             "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
             "online_passes": {"min": min(passes), "median": statistics.median(passes), "max": max(passes)},
             "chunks_per_frame_N": Ns[0],

@@ -110,6 +110,10 @@ typedef struct gsc_stats {
                                    (CUDA events on the context stream) */
 } gsc_stats;
 int gsc_get_stats(gsc_ctx *ctx, gsc_stats *out);
+/* Large batches run on two internal streams (even / odd frames); last_stage_ms adds both lanes up.
+ * gsc_stage_busy_ms gives the wall-clock time during which stage `stage` (index into last_stage_ms, 0..6)
+ * of the last batch ran on at least one of them (union of the two intervals; call after gsc_fetch_results). */
+int gsc_stage_busy_ms(gsc_ctx *ctx, int stage, double *ms_out);
 int gsc_reset_stats(gsc_ctx *ctx);
 
 /* ===================================================================== */

@@ -22,7 +22,7 @@ EXPORTS = [
     "ann_kdtree_create", "ann_kdtree_destroy", "ann_kdtree_search", "ann_kdtree_pri_search",
     "ann_kdtree_search_multi", "ann_kdtree_pri_search_multi",
     "gsc_last_error", "gsc_device_count", "gsc_create", "gsc_destroy", "gsc_ctx_device", "gsc_ctx_stream",
-    "gsc_synchronize", "gsc_get_stats", "gsc_reset_stats",
+    "gsc_synchronize", "gsc_get_stats", "gsc_stage_busy_ms", "gsc_reset_stats",
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
     "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
@@ -183,6 +183,12 @@ class Context:
         return dict(kernel_launches=int(s.kernel_launches), h2d_bytes=int(s.h2d_bytes),
                     d2h_bytes=int(s.d2h_bytes),
                     stage_ms={n: float(s.last_stage_ms[i]) for i, n in enumerate(STAGE_NAMES)})
+
+    def stage_busy_ms(self, stage: str) -> float:
+        """Wall-clock ms during which `stage` of the last batch ran on at least one of the two internal streams."""
+        v = C.c_double(0)
+        self._ck(self.L.gsc_stage_busy_ms(C.c_void_p(self.h), STAGE_NAMES.index(stage), C.byref(v)))
+        return v.value
 
     def reset_stats(self):
         self._ck(self.L.gsc_reset_stats(self.h))

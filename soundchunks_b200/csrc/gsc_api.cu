@@ -127,6 +127,7 @@ struct gsc_ctx {
     gsc_ctx *peer = nullptr;
     bool split = false;
     std::vector<int> idx_a, idx_b;   // frames of the last split batch handled by this context / by the peer
+    double stage_t[8] = {};          // start of stage i (ev[i]) in ms after the batch's fork event, filled at fetch
 };
 
 static std::atomic<int> g_rr{0};
@@ -916,7 +917,30 @@ static int collect_stage_times(gsc_ctx *c) {
     }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]) == cudaSuccess) c->stats.last_stage_ms[7] = ms;
+    for (int i = 0; i < 8; ++i) c->stage_t[i] = 0.0;
     cudaGetLastError();
+    return GSC_OK;
+}
+// stage boundaries of lane `c` relative to `origin` (an event recorded before both lanes started)
+static void collect_stage_offsets(gsc_ctx *c, cudaEvent_t origin) {
+    for (int i = 0; i < 8; ++i) {
+        float ms = 0;
+        c->stage_t[i] = (cudaEventElapsedTime(&ms, origin, c->ev[i]) == cudaSuccess) ? ms : 0.0;
+    }
+    cudaGetLastError();
+}
+
+// Wall-clock time (ms) during which stage `stage` (0..6, as in gsc_stats.last_stage_ms) of the last
+// gsc_encode_frames* batch was running on at least one of the context's two streams: the length of the
+// union of the two lanes' [start, end) intervals.  Equals last_stage_ms[stage] for a one-stream batch.
+extern "C" int gsc_stage_busy_ms(gsc_ctx *c, int stage, double *ms_out) {
+    if (!c || !ms_out || stage < 0 || stage > 6) return set_err(GSC_ERR_ARG, "bad arguments to gsc_stage_busy_ms");
+    if (!c->split || !c->peer) { *ms_out = c->stats.last_stage_ms[stage]; return GSC_OK; }
+    const double a0 = c->stage_t[stage], a1 = c->stage_t[stage + 1];
+    const double b0 = c->peer->stage_t[stage], b1 = c->peer->stage_t[stage + 1];
+    const double lo = a0 > b0 ? a0 : b0, hi = a1 < b1 ? a1 : b1;
+    const double overlap = hi > lo ? hi - lo : 0.0;
+    *ms_out = (a1 - a0) + (b1 - b0) - overlap;
     return GSC_OK;
 }
 
@@ -1047,6 +1071,8 @@ extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res
     for (int i : c->idx_b) rb.push_back(res[i]);
     TRY(fetch_one(c, (int)ra.size(), ra.data()));
     TRY(fetch_one(c->peer, (int)rb.size(), rb.data()));
+    collect_stage_offsets(c, c->ev[8]);          // ev[8] of the context = fork event of the batch
+    collect_stage_offsets(c->peer, c->ev[8]);
     for (size_t k = 0; k < ra.size(); ++k) res[c->idx_a[k]] = ra[k];
     for (size_t k = 0; k < rb.size(); ++k) res[c->idx_b[k]] = rb[k];
     return GSC_OK;

@@ -189,7 +189,7 @@ struct GscOnLayout {
     static constexpr unsigned X = 0;                                  // float [TP][D]
     static constexpr unsigned HX = X + GSC_ON_TP * D * 4;             // float [TP]
     static constexpr unsigned G = HX + GSC_ON_TP * 4;                 // int   [TP]
-    static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [B][L]
+    static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [L][B] (slot-major)
     static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B] entries per point (may exceed L: overflow)
     static constexpr unsigned THRW = LISTN + GSC_ON_B * 4;            // float [W][B] candidate thresholds (per-warp copy)
     static constexpr unsigned XLO = THRW + GSC_ON_B * (T / 32) * 4;   // float [W][B] slab x0 - r  (per-warp copy)
@@ -412,30 +412,42 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                 }
                 // pass (b): for those points only: certified lower bounds of the thread's centroids (FFMA2 filter),
                 // exact distance of the survivors, key into the point's candidate list
+                // two points per trip: their score chains are independent and hide each other's latency
                 while (hit) {
-                    const int b = __ffs(hit) - 1;
+                    const int b0 = __ffs(hit) - 1;
                     hit &= hit - 1;
-                    const float thr = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b) * 4u);
-                    float x[D];
-                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b) * D * 4, x);
-                    float s[CPT];
+                    const bool two = hit != 0;
+                    const int b1 = two ? __ffs(hit) - 1 : b0;
+                    hit &= hit - 1;   // (0 & -1 = 0 when there was no second bit)
+                    const float thr0 = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b0) * 4u);
+                    const float thr1 = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b1) * 4u);
+                    float x0[D], x1[D];
+                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b0) * D * 4, x0);
+                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b1) * D * 4, x1);
+                    float s0[CPT], s1[CPT];
                     {
-                        const float xq[DF] = {x[0], x[1], x[2], x[3]};
-                        gsc_filter_scores<CPT, DF>(xq, fcp, hp, s);
+                        const float xq0[DF] = {x0[0], x0[1], x0[2], x0[3]};
+                        const float xq1[DF] = {x1[0], x1[1], x1[2], x1[3]};
+                        gsc_filter_scores<CPT, DF>(xq0, fcp, hp, s0);
+                        gsc_filter_scores<CPT, DF>(xq1, fcp, hp, s1);
                     }
-                    unsigned m = 0;
+                    unsigned m0 = 0, m1 = 0;
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) m |= (s[j] >= thr) ? (1u << j) : 0u;
-                    while (m) {
-                        const int j = __ffs(m) - 1;
-                        m &= m - 1;
+                    for (int j = 0; j < CPT; ++j) { m0 |= (s0[j] >= thr0) ? (1u << j) : 0u; m1 |= (s1[j] >= thr1) ? (1u << j) : 0u; }
+                    if (!two) m1 = 0;
+                    while (m0 | m1) {
+                        const bool first0 = m0 != 0;
+                        const int j = __ffs(first0 ? m0 : m1) - 1;
+                        if (first0) m0 &= m0 - 1; else m1 &= m1 - 1;
+                        const int b = first0 ? b0 : b1;
                         float r[D];
                         gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
-                        const float d = gsc_ann_dist<D>(x, r);
+                        float d;
+                        if (first0) d = gsc_ann_dist<D>(x0, r); else d = gsc_ann_dist<D>(x1, r);
                         if (d == d) {
                             const unsigned long long kk = gsc_pack(__float_as_uint(d), idword(first + j));
                             const int slot = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);   // ~3 candidates per point: no contention
-                            if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(b * L + slot) * 8u, kk);
+                            if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(slot * B + b) * 8u, kk);   // [slot][point]: the resolver's lanes read without bank conflicts
                         }
                     }
                 }
@@ -461,9 +473,15 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                 int nl = 0;
                 auto scan_list = [&](bool skip_moved) -> unsigned long long {
                     unsigned long long best = GSC_KNONE;
-                    for (int e = 0; e < nl; ++e) {
-                        const unsigned long long kk = gsc_lds_u64(sb + Ly::LIST + (unsigned)(lane * L + e) * 8u);
-                        if (kk < best && !(skip_moved && gsc_lds_u8(sb + Ly::MFLAG + gsc_ks(kk)))) best = kk;
+                    for (int e = 0; e < nl; e += 4) {   // 4 independent loads per trip
+                        unsigned long long kq[4];
+                        int mv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) kq[q] = (e + q < nl) ? gsc_lds_u64(sb + Ly::LIST + (unsigned)((e + q) * B + lane) * 8u) : GSC_KNONE;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) mv[q] = (skip_moved && kq[q] != GSC_KNONE) ? gsc_lds_u8(sb + Ly::MFLAG + gsc_ks(kq[q])) : 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (kq[q] < best && !mv[q]) best = kq[q];
                     }
                     return best;
                 };
