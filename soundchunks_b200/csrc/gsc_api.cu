@@ -119,7 +119,7 @@ struct gsc_ctx {
     // device buffers
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
-        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg;
+        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke;
     HostBuf hpcm, hout;
     bool attr_set[4] = {false, false, false, false};
     // second lane: gsc_encode_frames splits a large batch over two streams so that the k-means tail of one
@@ -189,7 +189,7 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
-                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg};
+                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke};
     for (DevBuf *b : bufs) b->release();
     c->hpcm.release();
     c->hout.release();
@@ -544,6 +544,25 @@ static int stage_knnfit(gsc_ctx *c, bool want_band) {
     CU(cudaMemsetAsync(c->use.p, 0, 4 * fk, c->stream));
     CU(cudaMemsetAsync(c->overfull.p, 0, 4 * (size_t)c->F, c->stream));
     dim3 grid((c->maxN + 255) / 256, c->F);
+    static int dense = -1;   // GSC_KNNFIT_DENSE=1: the plain two-pass scan over all entries (A/B and cross-check)
+    if (dense < 0) { const char *e = getenv("GSC_KNNFIT_DENSE"); dense = (e && e[0] == '1') ? 1 : 0; }
+    if (!dense) {
+        TRY(c->kv.ensure(4 * fk * cs)); TRY(c->kn.ensure(4 * fk)); TRY(c->ke.ensure(4 * fk));
+        int r2 = 1;
+        while (r2 < c->Kmax) r2 <<= 1;
+        const size_t sm1 = 8 * (size_t)r2, sm2 = (size_t)c->Kmax * (4 * cs + 8);
+        DISPATCH_CS(cs, {
+            SMEM_OPTIN(k_knn_prep<CS>, sm1);
+            LAUNCH(c, k_knn_prep<CS>, c->F, 256, sm1, c->frames.as<GscFrame>(), c->bits, c->divider.as<int>(),
+                   c->dict.as<short>(), c->datten.as<unsigned char>(), c->kv.as<float>(), c->kn.as<float>(), c->ke.as<int>(),
+                   c->Kmax);
+            SMEM_OPTIN(k_knnfit_win<CS>, sm2);
+            LAUNCH(c, k_knnfit_win<CS>, grid, 256, sm2, c->frames.as<GscFrame>(), c->pcm.as<short>(), c->bits,
+                   c->divider.as<int>(), c->kv.as<float>(), c->kn.as<float>(), c->ke.as<int>(), c->best.as<int>(),
+                   c->use.as<int>(), want_band ? c->band.as<int>() : nullptr, c->overfull.as<int>(), c->Kmax);
+        });
+        return GSC_OK;
+    }
     size_t smem = sizeof(float) * (size_t)c->Kmax * cs;
     DISPATCH_CS(cs, {
         SMEM_OPTIN(k_knnfit<CS>, smem);

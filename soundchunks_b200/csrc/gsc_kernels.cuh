@@ -982,6 +982,179 @@ __global__ void __launch_bounds__(256) k_knnfit(const GscFrame *__restrict__ fra
 }
 
 // ---------------------------------------------------------------------------
+// K6, windowed form.  The Euclidean norm is the same for the four variants of an entry (sign and order
+// images), and d(q, v) >= (|q| - |v|)^2, so with the entries sorted by norm a query only has to visit the
+// window of entries whose norm lies within sqrt(dmin) (pass 1) or sqrt(dthr) (pass 2) of its own -- a few
+// percent of the dictionary.  k_knn_prep sorts one frame's de-quantised base variants by norm (bitonic, one
+// CTA); k_knnfit_win walks outwards from the query's own norm.  Results are those of k_knnfit: the same exact
+// distances, the same band threshold, the lowest ROW index inside the band (rows keep their entry numbers).
+// The margin covers the float evaluation of both norms and of the exact distance.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float gsc_norm_lb(float nq, float n) {
+    const float gap = fabsf(nq - n) - 1.0e-6f * (nq + n);   // both norms are within 5e-7 relative of the true ones
+    return gap > 0.0f ? gap * gap * (1.0f - 2e-6f) : 0.0f;
+}
+
+template <int CS>
+__global__ void __launch_bounds__(256) k_knn_prep(const GscFrame *__restrict__ frames, int bits,
+                                                  const int *__restrict__ divider,
+                                                  const short *__restrict__ dict,
+                                                  const unsigned char *__restrict__ datten,
+                                                  float *__restrict__ sV,   // [F][Kmax][CS] base variants, norm order
+                                                  float *__restrict__ sN,   // [F][Kmax] norms, ascending
+                                                  int *__restrict__ sE,     // [F][Kmax] entry of each position
+                                                  int Kmax) {
+    extern __shared__ unsigned long long s_key[];   // [R2] (norm bits << 32 | entry)
+    const GscFrame f = frames[blockIdx.x];
+    const long long fo = (long long)f.slot * Kmax;
+    const int R = f.R;
+    int R2 = 1;
+    while (R2 < R) R2 <<= 1;
+    GscLaw L;
+    L.init(1.0 / (double)divider[f.slot]);
+    const int obd = (1 << (bits - 1)) - 1;
+    for (int e = threadIdx.x; e < R2; e += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (e < R) {
+            float n2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < CS; ++j) {
+                const float v = (float)gsc_dequant(dict[(fo + e) * CS + j], obd, L.T[datten[fo + e]], false);
+                n2 = fmaf(v, v, n2);
+            }
+            key = ((unsigned long long)__float_as_uint(sqrtf(n2)) << 32) | (unsigned)e;
+        }
+        s_key[e] = key;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= R2; k2 <<= 1)
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < R2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = s_key[i], b = s_key[l];
+                    if ((a > b) == ((i & k2) == 0)) { s_key[i] = b; s_key[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int p = threadIdx.x; p < R; p += blockDim.x) {
+        const unsigned long long key = s_key[p];
+        const int e = (int)(key & 0xffffffffu);
+        sN[fo + p] = __uint_as_float((unsigned)(key >> 32));
+        sE[fo + p] = e;
+#pragma unroll
+        for (int j = 0; j < CS; ++j)
+            sV[(fo + p) * CS + j] = (float)gsc_dequant(dict[(fo + e) * CS + j], obd, L.T[datten[fo + e]], false);   // enc:932
+    }
+}
+
+template <int CS>
+__global__ void __launch_bounds__(256) k_knnfit_win(const GscFrame *__restrict__ frames,
+                                                    const short *__restrict__ pcm, int bits,
+                                                    const int *__restrict__ divider,
+                                                    const float *__restrict__ sV, const float *__restrict__ sN,
+                                                    const int *__restrict__ sE,
+                                                    int *__restrict__ best,      // [sumN]
+                                                    int *__restrict__ use,       // [F][Kmax], zeroed
+                                                    int *__restrict__ band,      // [sumN] or null
+                                                    int *__restrict__ overfull,  // [F], zeroed
+                                                    int Kmax) {
+    extern __shared__ float s_w[];   // [R][CS] variants | [R] norms | [R] entries (as int)
+    const GscFrame f = frames[blockIdx.y];
+    if ((long long)blockIdx.x * blockDim.x >= f.N) return;
+    const long long fo = (long long)f.slot * Kmax;
+    const int R = f.R;
+    float *s_v = s_w, *s_n = s_w + (size_t)R * CS;
+    int *s_e = reinterpret_cast<int *>(s_n + R);
+    for (int t = threadIdx.x; t < R * CS; t += blockDim.x) s_v[t] = sV[fo * CS + t];
+    for (int t = threadIdx.x; t < R; t += blockDim.x) { s_n[t] = sN[fo + t]; s_e[t] = sE[fo + t]; }
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= f.N) return;
+    const int i = n / f.C, ch = n - i * f.C;
+    const short *row = pcm + f.pcm_off + (long long)ch * f.stride + (long long)i * CS;
+    float q[CS];
+    float nq2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CS; ++j) { q[j] = (i * CS + j < f.S) ? (float)gsc_sample(row[j]) : 0.0f; nq2 = fmaf(q[j], q[j], nq2); }   // enc:949-950
+    const float nq = sqrtf(nq2);
+    // first position whose norm is >= the query's
+    int lo = 0, hi = R;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_n[mid] < nq) lo = mid + 1; else hi = mid; }
+    const int p0 = lo;
+
+    // pass 1: exact minimum, walking outwards from p0 while the norm bound can still beat it
+    float dmin = INFINITY;
+    {
+        int up = p0, dn = p0 - 1;
+        bool upok = up < R, dnok = dn >= 0;
+        while (upok || dnok) {
+            if (upok) {
+                if (gsc_norm_lb(nq, s_n[up]) > dmin) upok = false;
+                else {
+                    float v[CS];
+#pragma unroll
+                    for (int j = 0; j < CS; ++j) v[j] = s_v[up * CS + j];
+                    float d0, d1, d2, d3;
+                    gsc_variant_dists<CS>(q, v, d0, d1, d2, d3);
+                    dmin = fminf(dmin, fminf(fminf(d0, d1), fminf(d2, d3)));
+                    upok = ++up < R;
+                }
+            }
+            if (dnok) {
+                if (gsc_norm_lb(nq, s_n[dn]) > dmin) dnok = false;
+                else {
+                    float v[CS];
+#pragma unroll
+                    for (int j = 0; j < CS; ++j) v[j] = s_v[dn * CS + j];
+                    float d0, d1, d2, d3;
+                    gsc_variant_dists<CS>(q, v, d0, d1, d2, d3);
+                    dmin = fminf(dmin, fminf(fminf(d0, d1), fminf(d2, d3)));
+                    dnok = --dn >= 0;
+                }
+            }
+        }
+    }
+    // threshold: largest float d with in_band(d)
+    const double law = 1.0 / (double)divider[f.slot];
+    const float eps = gsc_knnfit_epsilon(bits, law);
+    const float fcs = (float)CS;
+    const float a = sqrtf(dmin / fcs);
+    unsigned blo = __float_as_uint(dmin), bhi = 0x7f800000u;  // in_band(lo) true, in_band(+inf) false
+    while (bhi - blo > 1u) {
+        const unsigned mid = blo + ((bhi - blo) >> 1);
+        if (gsc_in_band(a, __uint_as_float(mid), fcs, eps)) blo = mid; else bhi = mid;
+    }
+    const float dthr = __uint_as_float(blo);
+    // pass 2: lowest row inside the band and the band population, same walk with the band threshold
+    int bi = 0x7fffffff, nb = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+        int p = dir ? p0 - 1 : p0;
+        while (p >= 0 && p < R) {
+            if (gsc_norm_lb(nq, s_n[p]) > dthr) break;
+            float v[CS];
+#pragma unroll
+            for (int j = 0; j < CS; ++j) v[j] = s_v[p * CS + j];
+            float d0, d1, d2, d3;
+            gsc_variant_dists<CS>(q, v, d0, d1, d2, d3);
+            const bool b0 = d0 <= dthr, b1 = d1 <= dthr, b2 = d2 <= dthr, b3 = d3 <= dthr;
+            if (b0 | b1 | b2 | b3) {
+                nb += (int)b0 + (int)b1 + (int)b2 + (int)b3;
+                const int r0 = s_e[p] * 4 + (b0 ? 0 : b1 ? 1 : b2 ? 2 : 3);
+                bi = min(bi, r0);
+            }
+            p += dir ? -1 : 1;
+        }
+    }
+    if (bi == 0x7fffffff) bi = 0;  // only reachable with NaN distances
+    best[f.chunk_off + n] = bi;
+    atomicAdd(&use[fo + (bi >> 2)], 1);  // enc:962-964
+    if (band) band[f.chunk_off + n] = nb;
+    if (nb > GSC_BUCKET) atomicAdd(&overfull[f.slot], 1);
+}
+
+// ---------------------------------------------------------------------------
 // enc:970-977: prune unused entries, sort by use count (FreePascal quicksort
 // order), renumber; then emit the final dictionary and per-chunk index/attr.
 // One CTA per frame.  Dynamic smem: keys[Kmax] + items[Kmax] + stack[2*Kmax].
