@@ -255,3 +255,32 @@ def test_legacy_abi(ctx, oracle):
     assert idxs[0] == l[0] and errs[0] == d[0]
     ann.close()
     assert dd.shape[0] == pts.shape[0]
+
+
+def test_two_stream_batches_match_single_frames(ctx):
+    """Batches of >= 16 frames run on two internal streams (even / odd frames): results must be the frames'
+    own results, in the caller's order; the stage busy time is the union of the two lanes' intervals."""
+    frames = [_quiet(_audio(0.08 + 0.01 * (i % 5), 48000, 1 + (i % 2), 300 + i)) for i in range(21)]
+    frames[7] = _audio(0.004, 48000, 2, 5)                       # passthrough frame in the odd lane
+    batch = ctx.encode_frames(frames, chunk_bit_depth=12, chunks_per_frame=256)
+    st = ctx.stats()["stage_ms"]
+    busy = ctx.stage_busy_ms("kmeans")
+    assert 0.0 < busy <= st["kmeans"] + 1e-6                     # union <= sum of the lanes
+    for i in (0, 1, 7, 8, 19, 20):
+        one = ctx.encode_frames([frames[i]], chunk_bit_depth=12, chunks_per_frame=256)[0]
+        b = batch[i]
+        assert (b.N, b.R, b.divider, b.passes, b.err, b.overfull) == (one.N, one.R, one.divider, one.passes, one.err, one.overfull)
+        assert np.array_equal(b.dict, one.dict) and np.array_equal(b.datten, one.datten)
+        assert np.array_equal(b.index, one.index) and np.array_equal(b.attr, one.attr)
+
+
+def test_knnfit_windowed_equals_dense_on_large_dictionary(ctx, oracle):
+    """The norm-window search must return what the oracle's scan over all 4R rows returns, also for R = 4096."""
+    pcm = _quiet(_audio(1.2, 44100, 2, 61))
+    raw, attr, atten, feat, dst = oracle.make_chunks(pcm, 4, 12, 7)
+    rng = np.random.default_rng(9)
+    labels = rng.integers(0, 4096, len(feat)).astype(np.int32)   # any labelling gives a valid dictionary
+    d = oracle.build_dictionary(labels, raw, attr, 4096, 12, 7)
+    ref = oracle.knnfit(d["dict"], d["datten"], raw, 12, 7)
+    gpu = ctx.knnfit(d["dict"], d["datten"], pcm, 4, 12, 7)
+    assert np.array_equal(gpu["band"], ref["band"]) and np.array_equal(gpu["best"], ref["best_all"])
