@@ -244,6 +244,18 @@ int gsc_encode_frames_dev(gsc_ctx *ctx, const gsc_frame_desc *frames_devptr,
                           int n_frames, const gsc_params *params);
 int gsc_fetch_results(gsc_ctx *ctx, int n_frames, gsc_frame_result *results);
 
+/* the .gsc bytes (TFrame.SaveStream, enc:980-1107) of the last gsc_encode_frames* batch, packed
+ * on the device: header, attenuation nibbles, 8/12-bit dictionary samples, variable-length index codes.  The
+ * frames' streams are written to `out` back to back in frame order (enc:1208-1214); frame_bytes[n_frames] and
+ * *total are optional.  out = NULL only sizes.  sample_rate goes into the frame header (enc:994). */
+int gsc_fetch_stream(gsc_ctx *ctx, int n_frames, int sample_rate, uint8_t *out, int64_t cap,
+                     int64_t *frame_bytes, int64_t *total);
+/* encoder-side reconstruction (enc:487-522, 1518-1582) of the last batch compared with its PCM:
+ * sq_err[i] = sum over frame i of (src - dst)^2 in int16 units (exact), samples[i] = its sample count.
+ * PsyADelta (enc:1862-1880) = sqrt(sum sq_err / sum samples).  The PCM of the batch must still be on the
+ * device (always true after gsc_encode_frames; after gsc_encode_frames_dev while the caller keeps its buffer). */
+int gsc_fetch_quality(gsc_ctx *ctx, int n_frames, uint64_t *sq_err, int64_t *samples);
+
 /* Debug hook for the parity tests: 1 = the online k-means kernel scores every
  * centroid in the exact operation order instead of using its lower-bound
  * filter.  Results are identical by construction; the tests check that. */

@@ -26,7 +26,7 @@ EXPORTS = [
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
     "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters", "gsc_debug_seed_counters",
+    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters", "gsc_debug_seed_counters",
 ]
 
 
@@ -355,6 +355,22 @@ class Context:
                                    dict=d[:R].copy(), datten=a[:R].copy(), index=ix, attr=at,
                                    overfull=res[i].overfull))
         return out
+
+    def fetch_stream(self, n_frames: int, sample_rate: int):
+        """.gsc bytes of the last batch, packed on the device -> (bytes, per-frame sizes)."""
+        sizes = np.zeros(n_frames, np.int64)
+        total = C.c_int64(0)
+        self._ck(self.L.gsc_fetch_stream(C.c_void_p(self.h), n_frames, sample_rate, None, C.c_int64(0), _vp(sizes), C.byref(total)))
+        out = np.zeros(max(total.value, 1), np.uint8)
+        self._ck(self.L.gsc_fetch_stream(C.c_void_p(self.h), n_frames, sample_rate, _vp(out), C.c_int64(total.value), _vp(sizes), C.byref(total)))
+        return out[:total.value].tobytes(), sizes
+
+    def fetch_quality(self, n_frames: int):
+        """-> (sum of squared int16 errors per frame, samples per frame); PsyADelta = sqrt(sum / sum)."""
+        e2 = np.zeros(n_frames, np.uint64)
+        ns = np.zeros(n_frames, np.int64)
+        self._ck(self.L.gsc_fetch_quality(C.c_void_p(self.h), n_frames, _vp(e2), _vp(ns)))
+        return e2, ns
 
     def encode_frames_dev(self, dev_ptr: int, layout: Sequence[tuple], params: Params):
         """Device-resident PCM: layout = [(offset_samples, stride, channels, samples), ...] into the

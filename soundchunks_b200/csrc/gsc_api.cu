@@ -119,8 +119,9 @@ struct gsc_ctx {
     // device buffers
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
-        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke;
-    HostBuf hpcm, hout;
+        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke, sbytes, snb, sqerr;
+    HostBuf hpcm, hout, hstream;
+    const short *pcm_view = nullptr;   // PCM of the last batch on the device (own buffer or the caller's)
     bool attr_set[4] = {false, false, false, false};
     // second lane: gsc_encode_frames splits a large batch over two streams so that the k-means tail of one
     // half (few busy SMs) overlaps the seeding of the other
@@ -189,10 +190,11 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
-                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke};
+                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr};
     for (DevBuf *b : bufs) b->release();
     c->hpcm.release();
     c->hout.release();
+    c->hstream.release();
     for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -891,6 +893,7 @@ static int check_params(const gsc_params *p) {
 // DoFrame (enc:1433-1447) for the current batch; PCM already on the device.
 static int run_pipeline(gsc_ctx *c, const gsc_params *P) {
     const int D = 2 * P->chunk_size;
+    c->pcm_view = c->pcm.as<short>();
     c->bits = P->chunk_bit_depth;
     bool any_reduce = false;
     for (const GscFrame &f : c->h_frames) any_reduce |= f.K > 0;
@@ -1038,6 +1041,91 @@ static int launch_dev(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, co
     return rc;
 }
 
+
+// ---- the steps either side of the path, on the device -------------------------------
+static long long stream_cap(const gsc_ctx *c) {   // bytes per frame slot, multiple of 4
+    const long long v = 12 + (c->Kmax + 1) / 2 + 2LL * c->Kmax * c->cs + 4 + 2 * ((17LL * c->maxN + 15) / 16) + 8;
+    return (v + 3) & ~3LL;
+}
+// pack the .gsc bytes of one lane's frames into c->sbytes, sizes into c->snb, and bring both to the host
+static int pack_one(gsc_ctx *c, int sample_rate, std::vector<long long> &nb, const unsigned char **bytes, long long *cap_out) {
+    CU(cudaSetDevice(c->device));
+    const long long cap = stream_cap(c);
+    TRY(c->sbytes.ensure((size_t)cap * c->F)); TRY(c->snb.ensure(8 * (size_t)c->F));
+    DISPATCH_CS(c->cs, LAUNCH(c, k_pack_frames<CS>, c->F, 1024, 0, c->frames.as<GscFrame>(), c->bits, sample_rate,
+                              c->divider.as<int>(), c->newR.as<int>(), c->odict.as<short>(), c->odatten.as<unsigned char>(),
+                              c->oindex.as<int>(), c->oattr.as<unsigned char>(), c->sbytes.as<unsigned char>(), cap,
+                              c->snb.as<long long>(), c->Kmax));
+    nb.resize(c->F);
+    TRY(c->hstream.ensure((size_t)cap * c->F));
+    TRY(d2h(c, c->hstream.p, c->sbytes.p, (size_t)cap * c->F));
+    TRY(d2h(c, nb.data(), c->snb.p, 8 * (size_t)c->F));
+    TRY(sync(c));
+    *bytes = c->hstream.as<unsigned char>();
+    *cap_out = cap;
+    return GSC_OK;
+}
+
+extern "C" int gsc_fetch_stream(gsc_ctx *c, int n_frames, int sample_rate, uint8_t *out, int64_t cap, int64_t *frame_bytes,
+                                int64_t *total) {
+    FpGuard g;
+    if (!c || n_frames <= 0 || sample_rate <= 0 || sample_rate >= (1 << 24)) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_stream");
+    const bool split = c->split && c->peer;
+    if (n_frames != (split ? (int)(c->idx_a.size() + c->idx_b.size()) : c->F)) return set_err(GSC_ERR_ARG, "gsc_fetch_stream: frame count does not match the last batch");
+    std::vector<long long> na, nbv;
+    const unsigned char *ba = nullptr, *bb = nullptr;
+    long long ca = 0, cb = 0;
+    TRY(pack_one(c, sample_rate, na, &ba, &ca));
+    if (split) TRY(pack_one(c->peer, sample_rate, nbv, &bb, &cb));
+    long long sum = 0;
+    std::vector<long long> sz(n_frames);
+    for (int i = 0; i < n_frames; ++i) {
+        sz[i] = split ? ((i & 1) ? nbv[i >> 1] : na[i >> 1]) : na[i];
+        sum += sz[i];
+    }
+    if (total) *total = sum;
+    if (frame_bytes) for (int i = 0; i < n_frames; ++i) frame_bytes[i] = sz[i];
+    if (!out) return GSC_OK;                      // sizing call
+    if (cap < sum) return set_err(GSC_ERR_ARG, "gsc_fetch_stream: %lld bytes needed, room for %lld", sum, (long long)cap);
+    long long off = 0;
+    for (int i = 0; i < n_frames; ++i) {          // frames in index order (enc:1208-1214)
+        const unsigned char *src = split ? ((i & 1) ? bb + (long long)(i >> 1) * cb : ba + (long long)(i >> 1) * ca) : ba + (long long)i * ca;
+        memcpy(out + off, src, (size_t)sz[i]);
+        off += sz[i];
+    }
+    return GSC_OK;
+}
+
+static int quality_one(gsc_ctx *c, std::vector<unsigned long long> &e2) {
+    CU(cudaSetDevice(c->device));
+    if (!c->pcm_view) return set_err(GSC_ERR_ARG, "gsc_fetch_quality: no PCM of the last batch on the device");
+    TRY(c->sqerr.ensure(8 * (size_t)c->F));
+    CU(cudaMemsetAsync(c->sqerr.p, 0, 8 * (size_t)c->F, c->stream));
+    dim3 grid((c->maxN + 255) / 256, c->F);
+    DISPATCH_CS(c->cs, LAUNCH(c, k_reconstruct<CS>, grid, 256, 0, c->frames.as<GscFrame>(), c->pcm_view, c->bits,
+                              c->divider.as<int>(), c->odict.as<short>(), c->odatten.as<unsigned char>(), c->oindex.as<int>(),
+                              c->oattr.as<unsigned char>(), (short *)nullptr, c->sqerr.as<unsigned long long>(), c->Kmax));
+    e2.resize(c->F);
+    TRY(d2h(c, e2.data(), c->sqerr.p, 8 * (size_t)c->F));
+    return sync(c);
+}
+
+extern "C" int gsc_fetch_quality(gsc_ctx *c, int n_frames, uint64_t *sq_err, int64_t *samples) {
+    FpGuard g;
+    if (!c || n_frames <= 0 || !sq_err) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_quality");
+    const bool split = c->split && c->peer;
+    if (n_frames != (split ? (int)(c->idx_a.size() + c->idx_b.size()) : c->F)) return set_err(GSC_ERR_ARG, "gsc_fetch_quality: frame count does not match the last batch");
+    std::vector<unsigned long long> ea, eb;
+    TRY(quality_one(c, ea));
+    if (split) TRY(quality_one(c->peer, eb));
+    for (int i = 0; i < n_frames; ++i) {
+        const gsc_ctx *l = (split && (i & 1)) ? c->peer : c;
+        const int k = split ? (i >> 1) : i;
+        sq_err[i] = (split && (i & 1)) ? eb[k] : ea[k];
+        if (samples) samples[i] = (int64_t)l->h_frames[k].C * l->h_frames[k].S;
+    }
+    return GSC_OK;
+}
 
 // ---- two lanes per context ---------------------------------------------------------------------
 static int lanes_enabled() {

@@ -1214,6 +1214,159 @@ __global__ void __launch_bounds__(256) k_finalize(const GscFrame *__restrict__ f
 }
 
 // ---------------------------------------------------------------------------
+// the .gsc frame (TFrame.SaveStream, enc:980-1107) packed on the device, one CTA per frame.
+//   header 12 B | attenuation nibbles | dictionary samples (8-bit, or 12-bit pairs in 3 bytes) |
+//   u32 indexes per channel | LSB-first bit stream of per-chunk codes, flushed in 16-bit words
+// A chunk's code (enc:1054-1088): Negative(1) Reversed(1) NewHeader(1) [Header(2) if its group count differs
+// from the previous chunk's] then (groups+1) 3-bit groups of the index, most significant first; groups =
+// floor(bsr(index)/3).  Code lengths depend on the previous chunk only, so the bit offsets are an exclusive
+// prefix sum (block scan with a running carry) and every chunk ORs its bits into the zeroed output words.
+// out: [F][cap] bytes, cap a multiple of 4; nbytes[F].
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int gsc_index_groups(int index) { return index == 0 ? 0 : (31 - __clz(index)) / 3; }
+
+template <int CS>
+__global__ void __launch_bounds__(1024) k_pack_frames(const GscFrame *__restrict__ frames, int bits, int sample_rate,
+                                                      const int *__restrict__ divider, const int *__restrict__ newR,
+                                                      const short *__restrict__ odict, const unsigned char *__restrict__ odatten,
+                                                      const int *__restrict__ oindex, const unsigned char *__restrict__ oattr,
+                                                      unsigned char *__restrict__ out, long long cap,
+                                                      long long *__restrict__ nbytes, int Kmax) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const GscFrame f = frames[blockIdx.x];
+    const long long fo = (long long)f.slot * Kmax;
+    const int R = newR[f.slot];
+    unsigned char *o = out + (long long)f.slot * cap;
+    unsigned *ow = reinterpret_cast<unsigned *>(o);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // fixed-size sections
+    const int att_bytes = (R + 1) / 2;
+    const int smp_bytes = (bits == 8) ? R * CS : R * ((CS / 2) * 3 + (CS & 1) * 2);
+    const long long head = 12 + att_bytes + smp_bytes + 4;      // bytes before the bit stream
+    for (long long w = tid; w < cap / 4; w += blockDim.x) ow[w] = 0u;
+    __syncthreads();
+    if (tid == 0) {
+        o[0] = 1; o[1] = (unsigned char)f.C;                                   // StreamVersion, ChannelCount   enc:988-989
+        o[2] = (unsigned char)(R & 0xff); o[3] = (unsigned char)(R >> 8);      // ChunkCount | (BandCount-1)<<13 enc:990-991
+        o[4] = (unsigned char)bits; o[5] = (unsigned char)CS;                  // enc:992-993
+        o[6] = (unsigned char)(sample_rate & 0xff); o[7] = (unsigned char)((sample_rate >> 8) & 0xff);
+        o[8] = (unsigned char)((sample_rate >> 16) & 0xff); o[9] = 0;          // | ChunkBlend << 24             enc:994-995
+        const int dv = divider[f.slot];
+        o[10] = (unsigned char)(dv & 0xff); o[11] = (unsigned char)(dv >> 8);  // enc:996-997
+        const unsigned fl = (unsigned)(f.N / f.C);                             // enc:1048
+        unsigned char *q = o + 12 + att_bytes + smp_bytes;
+        q[0] = (unsigned char)(fl & 0xff); q[1] = (unsigned char)((fl >> 8) & 0xff);
+        q[2] = (unsigned char)((fl >> 16) & 0xff); q[3] = (unsigned char)(fl >> 24);
+    }
+    for (int j = tid; j < att_bytes; j += blockDim.x) {                        // enc:1003-1011
+        const int a0 = odatten[fo + 2 * j], a1 = (2 * j + 1 < R) ? odatten[fo + 2 * j + 1] : 0;
+        o[12 + j] = (unsigned char)((a0 << 4) | a1);
+    }
+    unsigned char *sp = o + 12 + att_bytes;
+    if (bits == 8) {                                                           // enc:1015-1018
+        for (int j = tid; j < R * CS; j += blockDim.x) sp[j] = (unsigned char)((odict[fo * CS + j] + 128) & 0xff);
+    } else {                                                                   // enc:1019-1039
+        constexpr int per = (CS / 2) * 3 + (CS & 1) * 2;
+        for (int e = tid; e < R; e += blockDim.x) {
+            const short *d = odict + (fo + e) * CS;
+            unsigned char *q = sp + (long long)e * per;
+#pragma unroll
+            for (int k = 0; k + 1 < CS; k += 2) {
+                const int s1 = d[k] + 2048, s2 = d[k + 1] + 2048;
+                q[(k / 2) * 3] = (unsigned char)(((s1 >> 4) & 0xf0) | ((s2 >> 8) & 0x0f));
+                q[(k / 2) * 3 + 1] = (unsigned char)(s1 & 0xff);
+                q[(k / 2) * 3 + 2] = (unsigned char)(s2 & 0xff);
+            }
+            if (CS & 1) { const int s1 = d[CS - 1] + 2048; q[(CS / 2) * 3] = (unsigned char)((s1 >> 4) & 0xf0); q[(CS / 2) * 3 + 1] = (unsigned char)(s1 & 0xff); }
+        }
+    }
+    if (tid == 0) s_carry = 0;
+    __syncthreads();   // header bytes are in place before the bit stream ORs into shared words
+    const int *idx = oindex + f.chunk_off;
+    const unsigned char *at = oattr + f.chunk_off;
+    for (int base = 0; base < f.N; base += blockDim.x) {
+        const int j = base + tid;
+        unsigned code = 0;
+        int len = 0;
+        if (j < f.N) {
+            const int ix = idx[j];
+            const int g = gsc_index_groups(ix);
+            const int pg = (j > 0) ? gsc_index_groups(idx[j - 1]) : -1;
+            code |= (unsigned)((at[j] >> 1) & 1) << len++;     // Negative
+            code |= (unsigned)(at[j] & 1) << len++;            // Reversed
+            if (g == pg) { ++len; }                            // NewHeader = 0
+            else { code |= 1u << len++; code |= (unsigned)g << len; len += 2; }
+            for (int k = g; k >= 0; --k) { code |= (unsigned)((ix >> (3 * k)) & 7) << len; len += 3; }
+        }
+        // exclusive prefix sum of the code lengths inside the CTA + running carry
+        long long incl = len;
+#pragma unroll
+        for (int of = 1; of < 32; of <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, of); if (lane >= of) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        long long wofs = 0;
+        for (int w = 0; w < warp; ++w) wofs += s_warp[w];
+        const long long carry = s_carry;
+        const long long bitpos = head * 8 + carry + wofs + incl - len;
+        if (len > 0) {
+            const unsigned long long v = (unsigned long long)code << (bitpos & 31);
+            atomicOr(ow + (bitpos >> 5), (unsigned)(v & 0xffffffffu));
+            if (v >> 32) atomicOr(ow + (bitpos >> 5) + 1, (unsigned)(v >> 32));
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) s_carry = carry + wofs + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const long long nbits = s_carry;
+        nbytes[f.slot] = head + 2 * ((nbits + 15) / 16);                        // flushed in 16-bit words, enc:1090-1105
+    }
+}
+
+// encoder-side reconstruction (enc:487-522, 1518-1582) and the squared error behind PsyADelta
+// (enc:1862-1880).  One thread per chunk; the error sum is a sum of squared int16 differences, exact in 64-bit
+// integers, so sqrt(sum / count) in Double equals the reference's sequential Double sum bit for bit.
+template <int CS>
+__global__ void __launch_bounds__(256) k_reconstruct(const GscFrame *__restrict__ frames, const short *__restrict__ pcm,
+                                                     int bits, const int *__restrict__ divider,
+                                                     const short *__restrict__ odict, const unsigned char *__restrict__ odatten,
+                                                     const int *__restrict__ oindex, const unsigned char *__restrict__ oattr,
+                                                     short *__restrict__ recon,              // same layout as pcm, or null
+                                                     unsigned long long *__restrict__ sqerr, // [F], zeroed
+                                                     int Kmax) {
+    const GscFrame f = frames[blockIdx.y];
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long e2 = 0;
+    if (n < f.N) {
+        const long long fo = (long long)f.slot * Kmax;
+        const int i = n / f.C, ch = n - i * f.C;
+        const int e = oindex[f.chunk_off + n];
+        const unsigned char a = oattr[f.chunk_off + n];
+        const bool rv = a & 1, ng = (a >> 1) & 1;
+        GscLaw L;
+        L.init(1.0 / (double)divider[f.slot]);
+        const int obd = (1 << (bits - 1)) - 1;
+        const double coeff = L.T[odatten[fo + e]];
+        const long long ro = f.pcm_off + (long long)ch * f.stride + (long long)i * CS;
+#pragma unroll
+        for (int j = 0; j < CS; ++j) {
+            if (i * CS + j < f.S) {
+                const double smp = gsc_dequant(odict[(fo + e) * CS + (rv ? CS - 1 - j : j)], obd, coeff, ng);   // enc:510
+                double r = rint(smp * 32767.0);                                                                  // enc:1638-1641
+                r = r < -32768.0 ? -32768.0 : (r > 32767.0 ? 32767.0 : r);
+                const int o16 = (int)r;
+                if (recon) recon[ro + j] = (short)o16;
+                const long long d = (long long)pcm[ro + j] - (long long)o16;
+                e2 += (unsigned long long)(d * d);
+            }
+        }
+    }
+    for (int of = 16; of > 0; of >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, of);
+    if ((threadIdx.x & 31) == 0 && e2) atomicAdd(&sqerr[f.slot], e2);
+}
+
+// ---------------------------------------------------------------------------
 // Lloyd assign: exact nearest centroid (ANN distance, lowest index on ties).
 // A cheap certified lower bound
 //   lb = (|c|^2)(1-g) - 2 x.c + (|x|^2)(1-g)   <=  d_exact

@@ -284,3 +284,32 @@ def test_knnfit_windowed_equals_dense_on_large_dictionary(ctx, oracle):
     ref = oracle.knnfit(d["dict"], d["datten"], raw, 12, 7)
     gpu = ctx.knnfit(d["dict"], d["datten"], pcm, 4, 12, 7)
     assert np.array_equal(gpu["band"], ref["band"]) and np.array_equal(gpu["best"], ref["best_all"])
+
+
+@pytest.mark.parametrize("nframes,ch,bits", [(3, 1, 12), (18, 2, 8), (17, 2, 12)])
+def test_device_stream_packer_and_quality(ctx, oracle, nframes, ch, bits):
+    """.gsc bytes packed on the device == the host writer's (enc:980-1107), and the
+    reconstruction error behind PsyADelta == the oracle's (enc:1862-1880); one-stream and two-stream batches."""
+    from soundchunks_b200 import host
+    frames = [_quiet(_audio(0.06 + 0.013 * (i % 4), 44100, ch, 500 + i)) for i in range(nframes)]
+    frames[1] = _audio(0.003, 44100, ch, 77)                      # passthrough frame, tiny dictionary
+    res = ctx.encode_frames(frames, chunk_bit_depth=bits, chunks_per_frame=256)
+    blob, sizes = ctx.fetch_stream(nframes, 44100)
+    want = [host.write_frame(r, ch, 4, bits, 44100) for r in res]
+    assert sizes.tolist() == [len(w) for w in want]
+    assert blob == b"".join(want)
+    dec, sr = oracle.decode(blob)                                 # and the reference decoder restatement reads it
+    assert sr == 44100 and dec.shape[1] == sum(f.shape[1] for f in frames)
+    e2, ns = ctx.fetch_quality(nframes)
+    tot = 0
+    for f, r, e, n in zip(frames, res, e2, ns):
+        rec = oracle.reconstruct_frame(oracle.FrameResult(r.N, r.R, r.divider, r.passes, r.err, r.dict, r.datten, r.index,
+                                                          r.attr, r.overfull), ch, f.shape[1], 4, bits)
+        d = f.astype(np.int64) - rec.astype(np.int64)
+        assert int(e) == int((d * d).sum()) and int(n) == f.size
+        tot += int(e)
+    allsrc = np.concatenate([f.ravel() for f in frames])
+    allrec = np.concatenate([oracle.reconstruct_frame(oracle.FrameResult(r.N, r.R, r.divider, r.passes, r.err, r.dict, r.datten,
+                                                                         r.index, r.attr, r.overfull), ch, f.shape[1], 4, bits).ravel()
+                             for f, r in zip(frames, res)])
+    assert np.sqrt(tot / float(ns.sum())) == oracle.psy_a_delta(allsrc, allrec)
