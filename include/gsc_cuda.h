@@ -233,6 +233,8 @@ typedef struct gsc_frame_result {
 /* Capacity (entries) the caller must provide for dict/datten of a frame. */
 int gsc_dict_capacity(const gsc_params *p, int channels, int samples);
 
+/* results may be NULL when only the packed stream / quality are wanted
+ * (gsc_fetch_stream, gsc_fetch_quality): nothing but those is copied back. */
 int gsc_encode_frames(gsc_ctx *ctx, const gsc_frame_desc *frames, int n_frames,
                       const gsc_params *params, gsc_frame_result *results);
 

@@ -372,6 +372,18 @@ class Context:
         self._ck(self.L.gsc_fetch_quality(C.c_void_p(self.h), n_frames, _vp(e2), _vp(ns)))
         return e2, ns
 
+    def encode_to_stream(self, frames: Sequence[np.ndarray], sample_rate: int, params: Optional[Params] = None, **kw):
+        """Host PCM in, .gsc bytes out (gsc_encode_frames without per-frame results + gsc_fetch_stream): what
+        an encoder front-end needs.  -> (bytes, per-frame sizes)"""
+        p = params if params is not None else default_params(**kw)
+        fr = [_pcm(f) for f in frames]
+        n = len(fr)
+        desc = (FrameDesc * n)()
+        for i, f in enumerate(fr):
+            desc[i] = FrameDesc(f.ctypes.data, f.shape[1], f.shape[0], f.shape[1])
+        self._ck(self.L.gsc_encode_frames(C.c_void_p(self.h), desc, n, C.byref(p), None))
+        return self.fetch_stream(n, sample_rate)
+
     def encode_frames_dev(self, dev_ptr: int, layout: Sequence[tuple], params: Params):
         """Device-resident PCM: layout = [(offset_samples, stride, channels, samples), ...] into the
         int16 buffer at dev_ptr.  Results stay on the device (fetch_results)."""

@@ -1168,6 +1168,20 @@ static int launch_lanes(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, 
     return GSC_OK;
 }
 
+// wait for the batch and collect its stage times without fetching per-frame results
+static int finish_batch(gsc_ctx *c) {
+    CU(cudaSetDevice(c->device));
+    TRY(sync(c));
+    collect_stage_times(c);
+    if (c->split && c->peer) {
+        CU(cudaStreamSynchronize(c->peer->stream));
+        collect_stage_times(c->peer);
+        collect_stage_offsets(c, c->ev[8]);
+        collect_stage_offsets(c->peer, c->ev[8]);
+    }
+    return GSC_OK;
+}
+
 extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res) {
     FpGuard g;
     if (!c || !res) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_results");
@@ -1188,8 +1202,12 @@ extern "C" int gsc_fetch_results(gsc_ctx *c, int n_frames, gsc_frame_result *res
 extern "C" int gsc_encode_frames(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P,
                                  gsc_frame_result *results) {
     FpGuard g;
-    if (!c || !frames || n_frames <= 0 || !results) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames");
+    if (!c || !frames || n_frames <= 0) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames");
     TRY(check_params(P));
+    if (!results) {   // the caller only wants the packed stream / quality (gsc_fetch_stream, gsc_fetch_quality)
+        TRY(launch_lanes(c, frames, n_frames, P, launch_host));
+        return finish_batch(c);
+    }
     static const bool trace = getenv("GSC_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     TRY(launch_lanes(c, frames, n_frames, P, launch_host));
