@@ -505,7 +505,7 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
         if (K <= 512) return online_launch<8, 8, 64>(c, tol, max_passes, fe);
         if (K <= 1024) return online_launch<8, 8, 128>(c, tol, max_passes, fe);
         if (K <= 2048) return online_launch<8, 16, 128>(c, tol, max_passes, fe);
-        if (K <= 4096) return online_launch<8, 16, 256>(c, tol, max_passes, fe);
+        if (K <= 4096) return online_launch<8, 16, 256>(c, tol, max_passes, fe);   // (8 x 512 threads measured 1.5x slower)
     } else if (D == 4) {
         if (K <= 256) return online_launch<4, 4, 64>(c, tol, max_passes, fe);
         if (K <= 512) return online_launch<4, 8, 64>(c, tol, max_passes, fe);
@@ -1058,8 +1058,9 @@ static int pack_one(gsc_ctx *c, int sample_rate, std::vector<long long> &nb, con
                               c->snb.as<long long>(), c->Kmax));
     nb.resize(c->F);
     TRY(c->hstream.ensure((size_t)cap * c->F));
-    TRY(d2h(c, c->hstream.p, c->sbytes.p, (size_t)cap * c->F));
-    TRY(d2h(c, nb.data(), c->snb.p, 8 * (size_t)c->F));
+    TRY(d2h(c, nb.data(), c->snb.p, 8 * (size_t)c->F));   // pageable destination: returns when the sizes are there
+    for (int i = 0; i < c->F; ++i)                          // only the bytes each frame uses
+        TRY(d2h(c, c->hstream.as<unsigned char>() + (size_t)cap * i, c->sbytes.as<unsigned char>() + (size_t)cap * i, (size_t)nb[i]));
     TRY(sync(c));
     *bytes = c->hstream.as<unsigned char>();
     *cap_out = cap;

@@ -191,10 +191,12 @@ struct GscOnLayout {
     static constexpr unsigned G = HX + GSC_ON_TP * 4;                 // int   [TP]
     static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [L][B] (slot-major)
     static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B] entries per point (may exceed L: overflow)
-    static constexpr unsigned THRW = LISTN + GSC_ON_B * 4;            // float [W][B] candidate thresholds (per-warp copy)
-    static constexpr unsigned XLO = THRW + GSC_ON_B * (T / 32) * 4;   // float [W][B] slab x0 - r  (per-warp copy)
-    static constexpr unsigned XHI = XLO + GSC_ON_B * (T / 32) * 4;    // float [W][B] slab x0 + r
-    static constexpr unsigned MOVED = XHI + GSC_ON_B * (T / 32) * 4;  // int   [B]
+    // thresholds and slabs of the batch: every warp computes and writes the same 32 values (benign: identical
+    // data) and reads them after its own __syncwarp, so one copy serves all warps without a block barrier
+    static constexpr unsigned THRW = LISTN + GSC_ON_B * 4;            // float [B] candidate thresholds
+    static constexpr unsigned XLO = THRW + GSC_ON_B * 4;              // float [B] slab x0 - r
+    static constexpr unsigned XHI = XLO + GSC_ON_B * 4;               // float [B] slab x0 + r
+    static constexpr unsigned MOVED = XHI + GSC_ON_B * 4;             // int   [B]
     static constexpr unsigned ROWS = MOVED + GSC_ON_B * 4;            // float [B][D]
     static constexpr unsigned WS = ROWS + GSC_ON_B * D * 4;           // int   [B]
     static constexpr unsigned ETB = WS + GSC_ON_B * 4;                // float [2][B]
@@ -397,17 +399,17 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const bool on = lane < nb && !force_exact;
                     // slab half-width: sqrt(U) widened for every rounding of the test and of the exact distance
                     const float rr = sqrtf(Umine) * 1.000002f + 4.0e-7f * fabsf(xb[0]) + 1e-30f;
-                    gsc_sts_f(sb + Ly::THRW + (unsigned)(warp * B + lane) * 4u, on ? gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * Umine : INFINITY);
-                    gsc_sts_f(sb + Ly::XLO + (unsigned)(warp * B + lane) * 4u, on ? xb[0] - rr : INFINITY);
-                    gsc_sts_f(sb + Ly::XHI + (unsigned)(warp * B + lane) * 4u, on ? xb[0] + rr : -INFINITY);
+                    gsc_sts_f(sb + Ly::THRW + (unsigned)lane * 4u, on ? gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * Umine : INFINITY);
+                    gsc_sts_f(sb + Ly::XLO + (unsigned)lane * 4u, on ? xb[0] - rr : INFINITY);
+                    gsc_sts_f(sb + Ly::XHI + (unsigned)lane * 4u, on ? xb[0] + rr : -INFINITY);
                 }
                 __syncwarp();
                 // pass (a): which points' slabs meet this thread's c0 range (one bit per point, branch-free)
                 unsigned hit = 0;
 #pragma unroll 8
                 for (int b = 0; b < B; ++b) {
-                    const float xl = gsc_lds_f(sb + Ly::XLO + (unsigned)(warp * B + b) * 4u);
-                    const float xh = gsc_lds_f(sb + Ly::XHI + (unsigned)(warp * B + b) * 4u);
+                    const float xl = gsc_lds_f(sb + Ly::XLO + (unsigned)b * 4u);
+                    const float xh = gsc_lds_f(sb + Ly::XHI + (unsigned)b * 4u);
                     hit |= ((xh >= c0lo) && (xl <= c0hi)) ? (1u << b) : 0u;
                 }
                 // pass (b): for those points only: certified lower bounds of the thread's centroids (FFMA2 filter),
@@ -419,8 +421,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const bool two = hit != 0;
                     const int b1 = two ? __ffs(hit) - 1 : b0;
                     hit &= hit - 1;   // (0 & -1 = 0 when there was no second bit)
-                    const float thr0 = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b0) * 4u);
-                    const float thr1 = gsc_lds_f(sb + Ly::THRW + (unsigned)(warp * B + b1) * 4u);
+                    const float thr0 = gsc_lds_f(sb + Ly::THRW + (unsigned)b0 * 4u);
+                    const float thr1 = gsc_lds_f(sb + Ly::THRW + (unsigned)b1 * 4u);
                     float x0[D], x1[D];
                     gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b0) * D * 4, x0);
                     gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b1) * D * 4, x1);
