@@ -216,8 +216,8 @@ struct GscOnLayout {
     static constexpr unsigned S2O = ((ERR + 8 + 15) / 16) * 16;       // u16   [KP] slot -> original centroid index
     static constexpr unsigned MFLAG = ((S2O + 2 * KP + 15) / 16) * 16; // u8    [KP]
     static constexpr unsigned RATE = ((MFLAG + KP + 15) / 16) * 16;   // float [KP]
-    static constexpr unsigned CNT = RATE + KP * 4;                    // int   [2][KP]
-    static constexpr unsigned C = ((CNT + 2 * KP * 4 + 15) / 16) * 16;  // float [KP][D]
+    static constexpr unsigned CNT = RATE + KP * 4;                    // int   [KP] hits of the running pass (+1), enc:717-721, 744, 754-758
+    static constexpr unsigned C = ((CNT + KP * 4 + 15) / 16) * 16;    // float [KP][D]
     static constexpr unsigned TOTAL = C + KP * D * 4;
     static_assert(TOTAL <= 227 * 1024, "shared memory budget of one SM");
 };
@@ -257,9 +257,10 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     // visits the warps whose range meets [x0 - sqrt(U), x0 + sqrt(U)] (a centroid outside that slab has
     // d >= (x0-c0)^2 > U).  Centroids drift during the passes; each thread keeps the exact [lo, hi] of its own
     // c0 values, so the test stays valid, only its selectivity depends on the order.  Keys carry the original
-    // index for the reference's tie order.  Bitonic sort of (c0, index) in the CNT region (32 KB, not yet in use).
+    // index for the reference's tie order.  Bitonic sort of (c0, index) in the row region (not yet in use).
     {
-        const unsigned sa = sb + Ly::CNT;
+        const unsigned sa = sb + Ly::C;   // KP x 8 bytes of the (still empty) row region
+        static_assert(D * 4 >= 8, "sort scratch fits the row region");
         for (int i = tid; i < KP; i += T) {
             unsigned kf = 0xffffffffu;
             if (i < K) { const float c0 = cf[(long long)i * D]; kf = (c0 == c0) ? gsc_fkey(c0) : 0xfffffffeu; }
@@ -311,8 +312,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         gsc_filter_set<CPT, DF>(fcp, hp, j, r, -0.5f * nc * (1.0f - GSC_ON_G));
         c0lo = fminf(c0lo, r[0]); c0hi = fmaxf(c0hi, r[0]);
     }
-    __syncthreads();   // the sort scratch (CNT) is free again
-    for (int j = tid; j < 2 * KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
+    for (int j = tid; j < KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
     for (int j = tid; j < KP / 4; j += T) gsc_sts_i(sb + Ly::MFLAG + 4u * j, 0);
     gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
     if (tid < B) gsc_sts_i(sb + Ly::LISTN + 4u * tid, 0);
@@ -326,12 +326,16 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     unsigned long long c_batches = 0, c_exh = 0, c_rounds = 0, c_over = 0, c_points = 0, c_cands = 0;
     int iter = 0;
     for (;;) {
-        const int odd = iter & 1;
-        const unsigned cnt_prev = sb + Ly::CNT + (odd ? 0u : (unsigned)KP * 4u);   // cnts[not Odd(iter)]
-        const unsigned cnt_cur = sb + Ly::CNT + (odd ? (unsigned)KP * 4u : 0u);    // cnts[Odd(iter)]
+        // The reference keeps cnts[2][K]: a pass reads cnts[not Odd(iter)] (the previous pass's hits + 1) for the
+        // rates, counts into cnts[Odd(iter)] and resets the array it read to 1.  The read array is only needed for
+        // the rates, which are tabulated here, so ONE array does both jobs: tabulate, reset to 1, count.
+        const unsigned cnt_cur = sb + Ly::CNT;
         const double prevErr = gsc_lds_d(sb + Ly::ERR);                            // uniform copy
         // rate of every centroid for this pass (cnt_prev is constant during a pass), enc:735
-        for (int j = tid; j < KP; j += T) gsc_sts_f(sb + Ly::RATE + 4u * j, gsc_rate(gsc_lds_i(cnt_prev + 4u * j)));
+        for (int j = tid; j < KP; j += T) {
+            gsc_sts_f(sb + Ly::RATE + 4u * j, gsc_rate(gsc_lds_i(cnt_cur + 4u * j)));
+            gsc_sts_i(cnt_cur + 4u * j, 1);
+        }
         __syncthreads();
         double e_run = 0.0;   // thread 32: enc:743 Double sum in point order, one batch behind the resolver
         int nbatch = 0, prev_nb = 0;
@@ -685,7 +689,6 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         }
         // ---- end of pass: enc:754-761 ----
         __syncthreads();
-        for (int j = tid; j < KP; j += T) gsc_sts_i(cnt_prev + 4u * j, 1);
         ++iter;
         if (tid == 32) {
             if (prev_nb) {
