@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsc_cuda", choices=["gsc_cuda", "reference"])
-    ap.add_argument("--frames", type=int, default=592, help="frames per GPU per step (4 waves of 148 one-CTA-per-SM frames)")
+    ap.add_argument("--frames", type=int, default=1184,
+                    help="frames per GPU per step (8 waves of 148 one-CTA-per-SM frames: 79 min of audio; the k-means tail of a\n"
+                         "step, where the last 100-pass frames run alone, is amortised over more frames)")
     ap.add_argument("--chunks-per-frame", type=int, default=4096)
     ap.add_argument("--bits", type=int, default=12)
     ap.add_argument("--mode", default="online", choices=["online", "lloyd"],
