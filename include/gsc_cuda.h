@@ -267,8 +267,7 @@ void gsc_debug_set_online_exact(int on);
 void gsc_debug_set_serial_scan(int on);
 /* Debug: counters of the last online k-means launch, 16 x uint64 per frame:
  * batches, points, re-filtered points, resolver rounds, full candidate lists,
- * candidates (lane 0), phase-1 cycles, phase-2 cycles, then the phase-1 split:
- * refresh, filter, barrier wait, exact keys; rest reserved. */
+ * candidates (lane 0); rest reserved (zero). */
 int gsc_debug_online_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
 /* Debug: cycles of the last seeding launch, 4 x uint64 per frame: seed pick,
  * distance pass, prefix scan, number of steps. */

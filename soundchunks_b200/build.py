@@ -32,8 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-fmad=false", "-Xcompiler", "-fPIC,-O2,-fvisibility=default", "-shared", "-o", SO]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
+    cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -41,7 +40,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libgsc_cuda.so")
+    spilled = online_spills(r.stdout + r.stderr)
+    if spilled:
+        os.remove(SO)
+        raise RuntimeError("k_online variants with register spills (the dispatch in gsc_api.cu must only use "
+                           "spill-free shapes): " + ", ".join(spilled))
     return SO
+
+
+def online_spills(ptxas_log: str) -> list:
+    """Names of k_online instantiations that ptxas compiled with spill stores.
+
+    The online k-means kernel sits at the 255-register limit; builds of its largest shape that spilled have
+    produced results that differ from the spill-free build, so a spilling shape is treated as a build error."""
+    bad, cur = [], None
+    for line in ptxas_log.splitlines():
+        if "Compiling entry function" in line:
+            cur = line.split("'")[1] if "'" in line else None
+        elif cur and "k_online" in cur and "spill stores" in line:
+            n = int(line.split("bytes stack frame,")[1].split("bytes spill stores")[0])
+            if n > 0:
+                bad.append(cur)
+    return bad
 
 
 def build_host(force: bool = False) -> str:

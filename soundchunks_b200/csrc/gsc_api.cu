@@ -499,18 +499,19 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     CU(cudaMemsetAsync(c->dbg.p, 0, 128 * (size_t)c->F, c->stream));
     const double tol = int_power10_neg(precision);
     const int K = c->Kmax, fe = force_exact_flag();
-    // CTA shape by dictionary size: small K -> small CTAs so that several frames share an SM
+    // CTA shape by dictionary size: small K -> small CTAs so that several frames share an SM.  Only shapes that
+    // compile without register spills are used (build.py checks).
     if (D == 8) {
         if (K <= 256) return online_launch<8, 4, 64>(c, tol, max_passes, fe);
-        if (K <= 512) return online_launch<8, 8, 64>(c, tol, max_passes, fe);
+        if (K <= 512) return online_launch<8, 4, 128>(c, tol, max_passes, fe);
         if (K <= 1024) return online_launch<8, 8, 128>(c, tol, max_passes, fe);
-        if (K <= 2048) return online_launch<8, 16, 128>(c, tol, max_passes, fe);
+        if (K <= 2048) return online_launch<8, 8, 256>(c, tol, max_passes, fe);
         if (K <= 4096) return online_launch<8, 16, 256>(c, tol, max_passes, fe);   // (8 x 512 threads measured 1.5x slower)
     } else if (D == 4) {
         if (K <= 256) return online_launch<4, 4, 64>(c, tol, max_passes, fe);
-        if (K <= 512) return online_launch<4, 8, 64>(c, tol, max_passes, fe);
+        if (K <= 512) return online_launch<4, 4, 128>(c, tol, max_passes, fe);
         if (K <= 1024) return online_launch<4, 8, 128>(c, tol, max_passes, fe);
-        if (K <= 2048) return online_launch<4, 16, 128>(c, tol, max_passes, fe);
+        if (K <= 2048) return online_launch<4, 8, 256>(c, tol, max_passes, fe);
         if (K <= 4096) return online_launch<4, 16, 256>(c, tol, max_passes, fe);
     }
     return set_err(GSC_ERR_UNSUPPORTED, "online k-means supports D in {4, 8} and K <= 4096 (got D=%d K=%d)", D, K);

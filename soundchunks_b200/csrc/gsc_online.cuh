@@ -14,28 +14,37 @@
 //   err   += sqrt(d / D)   (Single sqrt, Double accumulate)  enc:743
 //
 // Data placement (K = 4096, D = 8):
-//   shared memory  exact centroid rows K x 8 fp32 = 128 KB (the truth; read
-//                  only for exact scoring and updates), per-centroid rate
-//                  16 KB, counts 2 x 16 KB, moved flags 4 KB, point tile 8 KB,
-//                  candidate lists 8 KB
+//   shared memory  exact centroid rows K x 8 fp32 = 128 KB (the truth; read for
+//                  exact scoring, updates and the broadcast filter), h_c 16 KB,
+//                  per-centroid rate 16 KB, counts 16 KB, moved flags 4 KB,
+//                  point tile 8 KB, candidate lists 8 KB, survivor queues 8 KB
 //   registers      FILTER copy: first DF = 4 dims of the thread's CPT = 16
 //                  centroids (64 regs) + h_c = -0.5|c|^2(1-g) (16 regs)
 //   HBM            one 32-byte row per point per pass (streamed through smem)
 //
+// Codebook order: the kernel works on a copy sorted by c0 (first feature,
+// re-sorted at the start of every pass); a CELL is CPT consecutive slots and
+// belongs to one thread, consecutive cells to different warps.  A point visits
+// only the cells whose exact c0 range meets [x0 - sqrt(U), x0 + sqrt(U)].
+//
 // Schedule: points are taken in batches of B = 32 (lane b of warp 0 = point b).
-//  Phase 1 (all warps, codebook frozen at the batch start S0).  For every point
-//    each thread evaluates, over the first DF dimensions of its centroids,
-//        s_c = x.c + h_c                          (DF FFMAs per centroid)
+//  Phase 1 (all warps, codebook frozen at the batch start S0).  For every
+//    (cell, point) pair that passes the slab test the first DF dimensions give
+//        s_c = x.c + h_c                          (DF FMAs per centroid)
 //    which certifies the LOWER bound
 //        lb_c = |x|^2(1-g) - 2 s_c <= sum_{k<DF}(x_k-c_k)^2 <= d(x,c)
 //    (dropped squared terms are >= 0 and tiny -- the 1e-5-scaled cepstral
 //    features, enc:362; g = 2^-17 covers every rounding of both forms).
-//    Centroids with lb_c <= U_b are appended to the point's candidate list.
 //    U_b is the exact distance to the centroid the point chose in the previous
-//    pass (its seed cell in pass 0).
-//  Phase 1.5 (all warps): warp <-> point, lane <-> list slot.  Every candidate
-//    is scored in the exact operation order, its (d bits << 32 | index) key
-//    replaces the slot and a warp reduction leaves the point's best key.
+//    pass (its seed cell in pass 0).  Neighbouring points have neighbouring c0,
+//    so a batch hits a few cells with most of its points: cells with many points
+//    are evaluated by the whole warp (lane = point, the cell's rows broadcast
+//    from shared memory), the others by their owner from the register copy with
+//    FFMA2, two points per trip; a cost model picks the split per warp and batch.
+//    Centroids with lb_c <= U_b go to the warp's survivor queue; at the end of
+//    the phase the queue is scored densely, one survivor per lane, in the exact
+//    operation order, and the (d bits << 32 | index) keys are appended to the
+//    points' candidate lists.
 //  Phase 2 (warp 0) resolves the batch in ROUNDS.  In a round every unresolved
 //    lane t proposes the minimum of (a) its best list key among centroids not
 //    moved since S0 and (b) its best fresh key among centroids moved in this
@@ -217,7 +226,8 @@ struct GscOnLayout {
     static constexpr unsigned MFLAG = ((S2O + 2 * KP + 15) / 16) * 16; // u8    [KP]
     static constexpr unsigned RATE = ((MFLAG + KP + 15) / 16) * 16;   // float [KP]
     static constexpr unsigned CNT = RATE + KP * 4;                    // int   [KP] hits of the running pass (+1), enc:717-721, 744, 754-758
-    static constexpr unsigned C = ((CNT + KP * 4 + 15) / 16) * 16;    // float [KP][D]
+    static constexpr unsigned H = ((CNT + KP * 4 + 15) / 16) * 16;    // float [KP] h_c = -0.5|c|^2(1-g) over the filter dimensions
+    static constexpr unsigned C = H + KP * 4;                         // float [KP][D]
     static constexpr unsigned TOTAL = C + KP * D * 4;
     static_assert(TOTAL <= 227 * 1024, "shared memory budget of one SM");
 };
@@ -247,72 +257,37 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     const int K = f.K, N = f.N;
     if (K <= 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int first = tid * CPT;
+    // cell = CPT consecutive slots of the c0-sorted codebook.  Consecutive cells go to different warps (cell c ->
+    // warp c % W, lane c / W): neighbouring points have neighbouring c0, so a batch hits a few neighbouring cells
+    // and this spreads them over all warps.
+    const int cell = lane * (T / 32) + warp;
+    const int first = cell * CPT;
     const float *Xf = X + f.chunk_off * D;
     int *lab = labels + f.chunk_off;
     float *cf = cen + (long long)f.slot * Kmax * D;
 
-    // ---- the kernel works on a c0-SORTED copy of the codebook (c0 = first feature): slot s holds the
-    // centroid with the s-th smallest c0 at the start, a warp owns a contiguous c0 range, and a point only
-    // visits the warps whose range meets [x0 - sqrt(U), x0 + sqrt(U)] (a centroid outside that slab has
-    // d >= (x0-c0)^2 > U).  Centroids drift during the passes; each thread keeps the exact [lo, hi] of its own
-    // c0 values, so the test stays valid, only its selectivity depends on the order.  Keys carry the original
-    // index for the reference's tie order.  Bitonic sort of (c0, index) in the row region (not yet in use).
-    {
-        const unsigned sa = sb + Ly::C;   // KP x 8 bytes of the (still empty) row region
-        static_assert(D * 4 >= 8, "sort scratch fits the row region");
-        for (int i = tid; i < KP; i += T) {
-            unsigned kf = 0xffffffffu;
-            if (i < K) { const float c0 = cf[(long long)i * D]; kf = (c0 == c0) ? gsc_fkey(c0) : 0xfffffffeu; }
-            gsc_sts_u64(sa + 8u * i, ((unsigned long long)kf << 32) | (unsigned)i);
-        }
-        __syncthreads();
-        for (int k2 = 2; k2 <= KP; k2 <<= 1)
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < KP; i += T) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const unsigned long long va = gsc_lds_u64(sa + 8u * i), vb = gsc_lds_u64(sa + 8u * l);
-                        if ((va > vb) == ((i & k2) == 0)) { gsc_sts_u64(sa + 8u * i, vb); gsc_sts_u64(sa + 8u * l, va); }
-                    }
-                }
-                __syncthreads();
-            }
-        // slot -> original (kept), original -> slot (temporary, in the FK region) for the incoming labels
-        for (int i = tid; i < KP; i += T) {
-            const int o = (int)(gsc_lds_u64(sa + 8u * i) & 0xffffu);
-            gsc_sts_u16(sb + Ly::S2O + 2u * i, o);
-            gsc_sts_u16(sb + Ly::FK + 2u * o, i);
-            if (o == 0) gsc_sts_i(sb + Ly::SLOT0, i);
-        }
-        __syncthreads();
-        for (int j = tid; j < N; j += T) {   // incoming guesses: original index -> slot
-            int gg = lab[j];
-            gg = (gg < 0 || gg >= K) ? 0 : gg;
-            lab[j] = gsc_lds_u16(sb + Ly::FK + 2u * gg);
-        }
-        __syncthreads();
+    // ---- the kernel works on a c0-SORTED copy of the codebook (c0 = first feature): slot s holds the centroid
+    // with the s-th smallest c0, a thread owns a cell of CPT consecutive slots, and a point only visits the cells
+    // whose c0 range meets [x0 - sqrt(U), x0 + sqrt(U)] (a centroid outside that slab has d >= (x0-c0)^2 > U).
+    // Centroids drift while a pass runs; each thread keeps the exact [lo, hi] of its own c0 values, so the test
+    // stays valid, only its selectivity decays -- the order is restored at the start of every pass.  Keys carry
+    // the original index for the reference's tie order.
+    // Start: rows in original order (slot = original index); dead slots (index >= K) are NaN and never win.
+    for (int i = tid; i < KP; i += T) {
+        float r[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) r[k] = (i < K) ? cf[(long long)i * D + k] : __int_as_float(0x7fc00000);
+        gsc_sts_row<D>(sb + Ly::C + (unsigned)i * D * 4, r);
+        gsc_sts_u16(sb + Ly::S2O + 2u * i, i);
+        gsc_sts_i(sb + Ly::CNT + 4u * i, 1);  // enc:717-721
     }
-    // codebook -> shared rows + register filter copy; dead slots (original index >= K) are NaN and never win
-    static_assert(CPT % 2 == 0 && DF == 4, "packed filter copy");
+    for (int j = tid; j < N; j += T) {   // incoming guesses
+        const int gg = lab[j];
+        if (gg < 0 || gg >= K) lab[j] = 0;
+    }
+    static_assert(CPT % 2 == 0 && CPT <= 16 && DF == 4, "packed filter copy, 16-bit survivor masks");
     unsigned long long fcp[CPT / 2][DF], hp[CPT / 2];   // pairs of centroids: (2p, 2p+1)
     float c0lo = INFINITY, c0hi = -INFINITY;             // exact range of this thread's c0 values (NaN ignored)
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-        const int idx = first + j;
-        const int o = gsc_lds_u16(sb + Ly::S2O + 2u * idx);
-        float r[D];
-        float nc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            r[k] = (o < K) ? cf[(long long)o * D + k] : __int_as_float(0x7fc00000);
-            if (k < DF) nc = fmaf(r[k], r[k], nc);
-        }
-        gsc_sts_row<D>(sb + Ly::C + (unsigned)idx * D * 4, r);
-        gsc_filter_set<CPT, DF>(fcp, hp, j, r, -0.5f * nc * (1.0f - GSC_ON_G));
-        c0lo = fminf(c0lo, r[0]); c0hi = fmaxf(c0hi, r[0]);
-    }
-    for (int j = tid; j < KP; j += T) gsc_sts_i(sb + Ly::CNT + 4u * j, 1);  // enc:717-721
     for (int j = tid; j < KP / 4; j += T) gsc_sts_i(sb + Ly::MFLAG + 4u * j, 0);
     gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
     if (tid < B) gsc_sts_i(sb + Ly::LISTN + 4u * tid, 0);
@@ -322,7 +297,6 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     }
     __syncthreads();
 
-    unsigned long long c_ph1 = 0, c_ph2 = 0, c_t0 = 0, c_p0 = 0, c_flt = 0, c_b1 = 0, c_15 = 0, c_tx = 0, c_r3 = 0, c_r1 = 0, c_r2 = 0;
     unsigned long long c_batches = 0, c_exh = 0, c_rounds = 0, c_over = 0, c_points = 0, c_cands = 0;
     int iter = 0;
     for (;;) {
@@ -343,6 +317,63 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         for (int base = 0; base < N; base += GSC_ON_TP) {
             const int tn = min(GSC_ON_TP, N - base);
             __syncthreads();  // (A) previous tile fully consumed
+            // ---- pass start: restore the c0 order.  Bitonic sort of (20 leading bits of c0's order key, slot) -- an
+            // approximate order is all the slab test needs.  Scratch: the H region (rebuilt below) for the keys, FK for
+            // the old -> new slot map.  (Re-sorting more often inside the first passes was measured: it costs more
+            // than the sharper slabs save.)
+            if (base == 0) {
+                const unsigned sa = sb + Ly::H;
+                static_assert(KP <= 4096, "12-bit slots in the sort keys");
+                for (int i = tid; i < KP; i += T) {
+                    const float c0 = gsc_lds_f(sb + Ly::C + (unsigned)i * D * 4);
+                    gsc_sts_i(sa + 4u * i, (int)((((c0 == c0) ? gsc_fkey(c0) : 0xffffffffu) & 0xfffff000u) | (unsigned)i));
+                }
+                __syncthreads();
+                for (int k2 = 2; k2 <= KP; k2 <<= 1)
+                    for (int j = k2 >> 1; j > 0; j >>= 1) {
+                        for (int i = tid; i < KP; i += T) {
+                            const int l = i ^ j;
+                            if (l > i) {
+                                const unsigned va = (unsigned)gsc_lds_i(sa + 4u * i), vb = (unsigned)gsc_lds_i(sa + 4u * l);
+                                if ((va > vb) == ((i & k2) == 0)) { gsc_sts_i(sa + 4u * i, (int)vb); gsc_sts_i(sa + 4u * l, (int)va); }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                // gather this thread's new cell (rows, rates, counts, original indices), scatter after everybody has read
+                float rows[CPT][D], rt[CPT];
+                int so[CPT], cn[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const unsigned os = (unsigned)gsc_lds_i(sa + 4u * (unsigned)(first + j)) & 0xfffu;
+                    gsc_lds_row<D>(sb + Ly::C + os * D * 4, rows[j]);
+                    rt[j] = gsc_lds_f(sb + Ly::RATE + 4u * os);
+                    cn[j] = gsc_lds_i(cnt_cur + 4u * os);
+                    so[j] = gsc_lds_u16(sb + Ly::S2O + 2u * os);
+                    gsc_sts_u16(sb + Ly::FK + 2u * os, first + j);   // old slot -> new slot, for the labels
+                }
+                __syncthreads();
+                c0lo = INFINITY; c0hi = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const unsigned idx = (unsigned)(first + j);
+                    gsc_sts_row<D>(sb + Ly::C + idx * D * 4, rows[j]);
+                    gsc_sts_f(sb + Ly::RATE + 4u * idx, rt[j]);
+                    gsc_sts_i(cnt_cur + 4u * idx, cn[j]);
+                    gsc_sts_u16(sb + Ly::S2O + 2u * idx, so[j]);
+                    if (so[j] == 0) gsc_sts_i(sb + Ly::SLOT0, (int)idx);
+                    float nc = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < DF; ++k) nc = fmaf(rows[j][k], rows[j][k], nc);
+                    const float hv = -0.5f * nc * (1.0f - GSC_ON_G);
+                    gsc_sts_f(sb + Ly::H + 4u * idx, hv);
+                    gsc_filter_set<CPT, DF>(fcp, hp, j, rows[j], hv);
+                    c0lo = fminf(c0lo, rows[j][0]); c0hi = fmaxf(c0hi, rows[j][0]);
+                }
+                gsc_sts_i(sb + Ly::DIRTY + 4u * cell, 0);
+                for (int j = tid; j < N; j += T) lab[j] = gsc_lds_u16(sb + Ly::FK + 2u * (unsigned)lab[j]);   // labels are slots
+                __syncthreads();
+            }
             for (int t = tid; t < tn * D; t += T) gsc_sts_f(sb + Ly::X + 4u * t, Xf[(long long)base * D + t]);
             for (int t = tid; t < tn; t += T) {
                 int gg = lab[base + t];
@@ -359,12 +390,11 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
 
             for (int pos = 0; pos < tn; pos += B) {
                 const int nb = min(B, tn - pos);
-                if (tid == 0) c_t0 = clock64();
                 // ============ phase 0: refresh the filter copy of this thread's moved centroids ============
                 {
-                    const unsigned dirty = (unsigned)gsc_lds_i(sb + Ly::DIRTY + 4u * tid);
+                    const unsigned dirty = (unsigned)gsc_lds_i(sb + Ly::DIRTY + 4u * cell);
                     if (dirty) {
-                        gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
+                        gsc_sts_i(sb + Ly::DIRTY + 4u * cell, 0);
 #pragma unroll
                         for (int j = 0; j < CPT; ++j)
                             if (dirty & (1u << j)) {
@@ -384,7 +414,6 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         }
                     }
                 }
-                if (tid == 0) { c_tx = clock64(); c_p0 += c_tx - c_t0; }
                 // ============ phase 1: all warps, codebook frozen ============
                 float xb[D];              // lane b of every warp: point pos+b
                 float Umine = INFINITY;   // ... and its bound
@@ -410,56 +439,130 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                 __syncwarp();
                 // pass (a): which points' slabs meet this thread's c0 range (one bit per point, branch-free)
                 unsigned hit = 0;
-#pragma unroll 8
-                for (int b = 0; b < B; ++b) {
-                    const float xl = gsc_lds_f(sb + Ly::XLO + (unsigned)b * 4u);
-                    const float xh = gsc_lds_f(sb + Ly::XHI + (unsigned)b * 4u);
-                    hit |= ((xh >= c0lo) && (xl <= c0hi)) ? (1u << b) : 0u;
+#pragma unroll
+                for (int b4 = 0; b4 < B; b4 += 4) {
+                    const float4 xl = gsc_lds_f4(sb + Ly::XLO + (unsigned)b4 * 4u);
+                    const float4 xh = gsc_lds_f4(sb + Ly::XHI + (unsigned)b4 * 4u);
+                    hit |= ((xh.x >= c0lo) && (xl.x <= c0hi)) ? (1u << b4) : 0u;
+                    hit |= ((xh.y >= c0lo) && (xl.y <= c0hi)) ? (2u << b4) : 0u;
+                    hit |= ((xh.z >= c0lo) && (xl.z <= c0hi)) ? (4u << b4) : 0u;
+                    hit |= ((xh.w >= c0lo) && (xl.w <= c0hi)) ? (8u << b4) : 0u;
                 }
-                // pass (b): for those points only: certified lower bounds of the thread's centroids (FFMA2 filter),
-                // exact distance of the survivors, key into the point's candidate list
-                // two points per trip: their score chains are independent and hide each other's latency
-                while (hit) {
-                    const int b0 = __ffs(hit) - 1;
-                    hit &= hit - 1;
+                // pass (b): certified lower bounds of the cell's centroids for those points (s_c >= thr <=> lb_c <= U).
+                // Survivors go to the warp's queue and are scored exactly, one per lane, at the end of the phase.
+                constexpr int QCAP = (GSC_ON_B * GSC_ON_B * 8) / (4 * W);   // the FK region is free in phase 1
+                const unsigned q_a = sb + Ly::FK + (unsigned)warp * (unsigned)(QCAP * 4);
+                auto score_append = [&](int slot, int b) {
+                    float x[D], rw[D];
+                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b) * D * 4, x);
+                    gsc_lds_row<D>(sb + Ly::C + (unsigned)slot * D * 4, rw);
+                    const float d = gsc_ann_dist<D>(x, rw);
+                    if (d == d) {
+                        const unsigned long long kk = gsc_pack(__float_as_uint(d), idword(slot));
+                        const int sl = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);   // ~3 candidates per point: no contention
+                        if (sl < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(sl * B + b) * 8u, kk);   // [slot][point]: the resolver's lanes read without bank conflicts
+                    }
+                };
+                int qn = 0;   // entries in the warp's queue (warp-uniform)
+                const unsigned lt_mask = (1u << lane) - 1u;
+                // all lanes call together; bits 0..15 of m are survivors of point ba, bits 16..31 of point bb
+                auto push = [&](unsigned m, int fo, int ba, int bb) {
+                    unsigned any;
+                    while ((any = __ballot_sync(FULL, m != 0)) != 0) {
+                        if (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int off = qn + __popc(any & lt_mask);
+                            const int slot = fo + (j & 15), b = (j < 16) ? ba : bb;
+                            if (off < QCAP) gsc_sts_i(q_a + 4u * (unsigned)off, (slot << 5) | b);
+                            else score_append(slot, b);
+                        }
+                        qn += __popc(any);
+                    }
+                };
+                // A batch of neighbouring points hits the same few cells with most of its points; left to the owner
+                // threads, one lane would work through 20+ points while its warp idles.  Cells with many points are
+                // therefore evaluated by the whole warp, lane b = point b, the cell's rows broadcast from shared
+                // memory; the others by their owners from the register copy, two points per trip.  The split point is
+                // chosen per warp and batch from a cost model (CH per broadcast cell, CT per owner trip).
+                const int cnt = __popc(hit);
+                int hotT = 1;
+                {
+                    constexpr int CH = 170, CT = 450;
+                    const int wmax = (int)__reduce_max_sync(FULL, (unsigned)cnt);
+                    int bestc = 0x7fffffff;
+                    const int opts[8] = {1, 3, 5, 7, 9, 13, 17, 33};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int nh = __popc(__ballot_sync(FULL, cnt >= opts[i]));
+                        const int c = nh * CH + ((min(opts[i] - 1, wmax) + 1) / 2) * CT;
+                        if (c < bestc) { bestc = c; hotT = opts[i]; }
+                    }
+                }
+                const bool hot = cnt >= hotT;
+                for (unsigned hm = __ballot_sync(FULL, hot); hm; hm &= hm - 1) {
+                    const int o = __ffs(hm) - 1;
+                    const unsigned ho = __shfl_sync(FULL, hit, o);
+                    const int fo = (o * W + warp) * CPT;   // first slot of the owner's cell
+                    const float thr = gsc_lds_f(sb + Ly::THRW + (unsigned)lane * 4u);
+                    unsigned m = 0;
+#pragma unroll
+                    for (int j4 = 0; j4 < CPT; j4 += 4) {
+                        const float4 h4 = gsc_lds_f4(sb + Ly::H + (unsigned)(fo + j4) * 4u);
+                        const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
+                        float4 c4[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) c4[j] = gsc_lds_f4(sb + Ly::C + (unsigned)(fo + j4 + j) * D * 4);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float sc = fmaf(xb[3], c4[j].w, fmaf(xb[2], c4[j].z, fmaf(xb[1], c4[j].y, fmaf(xb[0], c4[j].x, hh[j]))));
+                            m |= (sc >= thr) ? (1u << (j4 + j)) : 0u;
+                        }
+                    }
+                    if (!((ho >> lane) & 1u)) m = 0;
+                    push(m, fo, lane, lane);
+                }
+                if (hot) hit = 0;
+                __syncwarp();
+                // two points per trip: their score chains are independent and hide each other's latency.  The warp makes
+                // as many trips as its busiest lane needs (lanes without work carry empty masks) so that the queue
+                // pushes are warp-wide.
+                const int trips = (int)__reduce_max_sync(FULL, (unsigned)((__popc(hit) + 1) >> 1));
+                for (int tr = 0; tr < trips; ++tr) {
+                    const bool one = hit != 0;
+                    const int b0 = one ? __ffs(hit) - 1 : 0;
+                    hit &= hit - 1;   // (0 & -1 = 0 when there is no bit left)
                     const bool two = hit != 0;
                     const int b1 = two ? __ffs(hit) - 1 : b0;
-                    hit &= hit - 1;   // (0 & -1 = 0 when there was no second bit)
+                    hit &= hit - 1;
                     const float thr0 = gsc_lds_f(sb + Ly::THRW + (unsigned)b0 * 4u);
                     const float thr1 = gsc_lds_f(sb + Ly::THRW + (unsigned)b1 * 4u);
-                    float x0[D], x1[D];
-                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b0) * D * 4, x0);
-                    gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b1) * D * 4, x1);
                     float s0[CPT], s1[CPT];
                     {
-                        const float xq0[DF] = {x0[0], x0[1], x0[2], x0[3]};
-                        const float xq1[DF] = {x1[0], x1[1], x1[2], x1[3]};
+                        const float4 v0 = gsc_lds_f4(sb + Ly::X + (unsigned)(pos + b0) * D * 4);
+                        const float4 v1 = gsc_lds_f4(sb + Ly::X + (unsigned)(pos + b1) * D * 4);
+                        const float xq0[DF] = {v0.x, v0.y, v0.z, v0.w};
+                        const float xq1[DF] = {v1.x, v1.y, v1.z, v1.w};
                         gsc_filter_scores<CPT, DF>(xq0, fcp, hp, s0);
                         gsc_filter_scores<CPT, DF>(xq1, fcp, hp, s1);
                     }
                     unsigned m0 = 0, m1 = 0;
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) { m0 |= (s0[j] >= thr0) ? (1u << j) : 0u; m1 |= (s1[j] >= thr1) ? (1u << j) : 0u; }
+                    if (!one) m0 = 0;
                     if (!two) m1 = 0;
-                    while (m0 | m1) {
-                        const bool first0 = m0 != 0;
-                        const int j = __ffs(first0 ? m0 : m1) - 1;
-                        if (first0) m0 &= m0 - 1; else m1 &= m1 - 1;
-                        const int b = first0 ? b0 : b1;
-                        float r[D];
-                        gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
-                        float d;
-                        if (first0) d = gsc_ann_dist<D>(x0, r); else d = gsc_ann_dist<D>(x1, r);
-                        if (d == d) {
-                            const unsigned long long kk = gsc_pack(__float_as_uint(d), idword(first + j));
-                            const int slot = gsc_atoms_add(sb + Ly::LISTN + 4u * b, 1);   // ~3 candidates per point: no contention
-                            if (slot < L) gsc_sts_u64(sb + Ly::LIST + (unsigned)(slot * B + b) * 8u, kk);   // [slot][point]: the resolver's lanes read without bank conflicts
-                        }
+                    push(m0 | (m1 << 16), first, b0, b1);
+                }
+                // exact scores of the queued survivors, one per lane
+                __syncwarp();
+                {
+                    const int qe = min(qn, QCAP);
+                    for (int i = lane; i < qe; i += 32) {
+                        const int e = gsc_lds_i(q_a + 4u * (unsigned)i);
+                        score_append(e >> 5, e & 31);
                     }
                 }
-                if (tid == 0) { const unsigned long long t1 = clock64(); c_flt += t1 - c_tx; c_tx = t1; }
                 __syncthreads();   // ---- bar 1: candidate lists complete ----
-                if (tid == 0) { const unsigned long long t1 = clock64(); c_b1 += t1 - c_tx; c_ph1 += t1 - c_t0; c_t0 = t1; }
                 // thread 32 adds the error terms of the previous batch while warp 0 opens this one
                 if (tid == 32 && prev_nb) {
                     const unsigned eb = sb + Ly::ETB + (unsigned)(((nbatch - 1) & 1) * B) * 4u;
@@ -499,10 +602,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     abest = scan_list(false);
                 }
                 const unsigned etb = sb + Ly::ETB + (unsigned)((nbatch & 1) * B) * 4u;
-                if (tid == 0) { const unsigned long long t1 = clock64(); c_15 += t1 - c_t0; c_tx = t1; }
                 for (;;) {
                     if (warp == 0) {
-                        if (tid == 0) c_tx = clock64();
                         if (pending == GSC_MODE_SCAN) {
                             // ---- R3: first conflicting lane, commit the lanes before it ----
                             unsigned firstc = 32u;
@@ -515,6 +616,12 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                             int already = 0;
                             if (commit) {
                                 gsc_sts_row<D>(sb + Ly::C + (unsigned)w * D * 4, rn);
+                                {
+                                    float nc = 0.0f;
+#pragma unroll
+                                    for (int k = 0; k < DF; ++k) nc = fmaf(rn[k], rn[k], nc);
+                                    gsc_sts_f(sb + Ly::H + 4u * (unsigned)w, -0.5f * nc * (1.0f - GSC_ON_G));
+                                }
                                 gsc_sts_i(cnt_cur + 4u * w, gsc_lds_i(cnt_cur + 4u * w) + 1);            // enc:744
                                 lab[base + pos + lane] = w;                                               // enc:742
                                 gsc_sts_f(etb + 4u * lane, sqrtf(__uint_as_float(gsc_kd(key)) / (float)D));  // enc:743 (term)
@@ -577,7 +684,6 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                             }
                             c_exh += __popc(badmask);
                         }
-                        if (tid == 0) { const unsigned long long t1 = clock64(); c_r3 += t1 - c_tx; c_tx = t1; }
                         // ---- R1: proposals of the unresolved lanes ----
                         if (t0 >= nb) {
                             // hand over to the next batch
@@ -619,7 +725,6 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                             }
                         }
                     }
-                    if (tid == 0) { const unsigned long long t1 = clock64(); c_r1 += t1 - c_tx; c_tx = t1; }
                     __syncthreads();   // ---- bar 2: proposals / request visible ----
                     const int mode = gsc_lds_i(sb + Ly::MODE);
                     if (mode == GSC_MODE_DONE) break;
@@ -680,9 +785,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                         }
                     }
                     __syncthreads();   // ---- bar 3: round results complete ----
-                    if (tid == 0) { const unsigned long long t1 = clock64(); c_r2 += t1 - c_tx; c_tx = t1; }
                 }
-                if (tid == 0) c_ph2 += clock64() - c_t0;
                 prev_nb = nb;
                 ++nbatch;
             }
@@ -722,8 +825,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
         err_out[f.slot] = gsc_lds_d(sb + Ly::ERR);
         if (dbg) {
             unsigned long long *o = dbg + (long long)f.slot * 16;
-            o[0] = c_batches; o[1] = c_points; o[2] = c_exh; o[3] = c_rounds; o[4] = c_over; o[5] = c_cands; o[6] = c_ph1; o[7] = c_ph2;
-            o[8] = c_p0; o[9] = c_flt; o[10] = c_b1; o[11] = c_15; o[12] = c_r3; o[13] = c_r1; o[14] = c_r2;
+            o[0] = c_batches; o[1] = c_points; o[2] = c_exh; o[3] = c_rounds; o[4] = c_over; o[5] = c_cands;
         }
     }
 }

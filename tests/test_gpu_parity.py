@@ -112,7 +112,7 @@ def test_yakmo_random_init_and_iters(ctx, oracle):
     assert np.array_equal(l_gpu, l_ref)
 
 
-@pytest.mark.parametrize("K,seconds,passes", [(256, 0.25, 100), (100, 0.1, 7), (4096, 0.6, 4), (700, 0.3, 20)])
+@pytest.mark.parametrize("K,seconds,passes", [(256, 0.25, 100), (100, 0.1, 7), (4096, 0.6, 4), (700, 0.3, 20), (1500, 0.4, 8), (400, 0.2, 12)])
 def test_online_kmeans_bit_exact(ctx, oracle, K, seconds, passes):
     pcm, raw, attr, feat = _features(oracle, seconds, ch=2 if K == 4096 else 1)
     c0, _, _ = oracle.yakmo(feat, K)

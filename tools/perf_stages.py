@@ -30,7 +30,4 @@ for K, bits in cfgs:
     cn = ctx.online_counters(min(nf, 8)).astype(float)
     for r in cn[:4]:
         b, p, e, rd, ov, ca = r[:6]
-        print(f"   cycles/batch: phase1 {r[6] / max(b, 1):.0f} phase2 {r[7] / max(b, 1):.0f}  cycles/point {(r[6] + r[7]) / max(p, 1):.0f}")
-        print(f"   phase1 split/batch: refresh {r[8] / max(b, 1):.0f} filter {r[9] / max(b, 1):.0f} bar1 wait {r[10] / max(b, 1):.0f} keys {r[11] / max(b, 1):.0f}")
-        print(f"   phase2 split/batch: list close {r[11] / max(b, 1):.0f} R3 {r[12] / max(b, 1):.0f} R1 {r[13] / max(b, 1):.0f} R2+barriers {r[14] / max(b, 1):.0f}")
         print(f"   batches {b:.0f} points {p:.0f} exhaustive {e:.0f} rounds/batch {rd / max(b, 1):.2f} full lists {ov:.0f} cands/pt {ca / max(p, 1):.2f}")
