@@ -235,11 +235,9 @@ struct GscScanSmem {
     int w0[GSC_SEED_THREADS / 32], w1[GSC_SEED_THREADS / 32];
     int wv[GSC_SEED_THREADS / 32];
     unsigned long long n_rounds, n_serial;   // debug counters
-    float run;      // running sum before element `pos`
+    float run;      // running sum handed back by the serial chain
     float before;   // value of the sum just before the first uncertified element of the round
     float addend;   // ... and that element itself (from its owner's registers)
-    int pos;        // first element not yet final
-    int addidx;     // element that the last round added with a real float addition (-1: none)
 };
 
 __device__ __forceinline__ void gsc_scan_compose(int &f0, int &f1, int g0, int g1) {
@@ -252,7 +250,10 @@ __device__ __forceinline__ void gsc_scan_compose(int &f0, int &f1, int g0, int g
 __device__ float gsc_seq_prefix(const float *__restrict__ a, float *__restrict__ r, int N, GscScanSmem &sm) {
     constexpr int E = GSC_SCAN_E;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { sm.run = 0.0f; sm.pos = 0; sm.addidx = -1; }
+    // running sum before element `pos`, first element not yet final, element that the last round added with a
+    // real float addition (-1: none): every thread keeps its own (identical) copy
+    float run = 0.0f;
+    int pos = 0, addidx = -1;
     __syncthreads();
     for (int wbase = 0; wbase < N; wbase += GSC_SCAN_WIN) {
         const int wend = min(N, wbase + GSC_SCAN_WIN);
@@ -274,9 +275,6 @@ __device__ float gsc_seq_prefix(const float *__restrict__ a, float *__restrict__
 #pragma unroll
         for (int e = 0; e < E; ++e) out[e] = 0.0f;
         for (;;) {   // rounds
-            const int pos = sm.pos;       // uniform
-            const float run = sm.run;
-            const int addidx = sm.addidx;
             // the element the previous round added for real belongs to someone: its value is the running sum
 #pragma unroll
             for (int e = 0; e < E; ++e) if (j0 + e == addidx) out[e] = run;
@@ -339,7 +337,20 @@ __device__ float gsc_seq_prefix(const float *__restrict__ a, float *__restrict__
                 if (lane == 31) { sm.w0[warp] = s0; sm.w1[warp] = s1; }
                 __syncthreads();
                 int x0 = 0, x1 = 0;
-                for (int w = 0; w < warp; ++w) gsc_scan_compose(x0, x1, sm.w0[w], sm.w1[w]);
+                {
+                    // composition of the warps before this one: a log-step scan of the per-warp functions over the
+                    // lanes (lane w holds warp w's function) instead of a serial walk through shared memory
+                    constexpr int NW = GSC_SEED_THREADS / 32;
+                    int a0 = (lane < NW) ? sm.w0[lane] : 0, a1 = (lane < NW) ? sm.w1[lane] : 0;
+#pragma unroll
+                    for (int o = 1; o < NW; o <<= 1) {
+                        const int p0 = __shfl_up_sync(0xffffffffu, a0, o), p1 = __shfl_up_sync(0xffffffffu, a1, o);
+                        if (lane >= o) { int q0 = p0, q1 = p1; gsc_scan_compose(q0, q1, a0, a1); a0 = q0; a1 = q1; }
+                    }
+                    const int src = warp > 0 ? warp - 1 : 0;
+                    const int b0 = __shfl_sync(0xffffffffu, a0, src), b1 = __shfl_sync(0xffffffffu, a1, src);
+                    if (warp > 0) { x0 = b0; x1 = b1; }
+                }
                 {
                     int e0 = __shfl_up_sync(0xffffffffu, s0, 1), e1 = __shfl_up_sync(0xffffffffu, s1, 1);
                     if (lane == 0) { e0 = 0; e1 = 0; }
@@ -398,22 +409,18 @@ __device__ float gsc_seq_prefix(const float *__restrict__ a, float *__restrict__
                         }
                         if (j < lim) r[j] = mine;
                     }
-                    if (lane == 0) { sm.run = rr; sm.pos = lim; sm.addidx = -1; }
+                    if (lane == 0) sm.run = rr;
                 }
                 __syncthreads();
+                run = sm.run; pos = lim; addidx = -1;
                 // the chain wrote r[vv .. lim): their owners take the values over (the window is stored at its end)
 #pragma unroll
                 for (int e = 0; e < E; ++e) { const int j = j0 + e; if (j >= vv && j < lim) out[e] = r[j]; }
+            } else if (vv < wend) {
+                run = sm.before + sm.addend;   // the one real float addition
+                pos = vv + 1; addidx = vv;
             } else {
-                if (tid == 0) {
-                    if (vv < wend) {
-                        const float nv = sm.before + sm.addend;   // the one real float addition
-                        sm.run = nv; sm.pos = vv + 1; sm.addidx = vv;
-                    } else {
-                        sm.run = sm.before; sm.pos = wend; sm.addidx = -1;
-                    }
-                }
-                __syncthreads();
+                run = sm.before; pos = wend; addidx = -1;
             }
         }
         // store the window
@@ -427,9 +434,8 @@ __device__ float gsc_seq_prefix(const float *__restrict__ a, float *__restrict__
         }
         __syncthreads();
     }
-    const float total = sm.run;
     __syncthreads();
-    return total;
+    return run;
 }
 
 template <int D>
