@@ -255,23 +255,32 @@ __device__ float gsc_seq_prefix(const float *__restrict__ a, float *__restrict__
     float run = 0.0f;
     int pos = 0, addidx = -1;
     __syncthreads();
-    for (int wbase = 0; wbase < N; wbase += GSC_SCAN_WIN) {
-        const int wend = min(N, wbase + GSC_SCAN_WIN);
-        const int j0 = wbase + tid * E;
-        const bool vec = (j0 + E <= N) && ((reinterpret_cast<unsigned long long>(a + j0) & 15ull) == 0ull) &&
-                         ((reinterpret_cast<unsigned long long>(r + j0) & 15ull) == 0ull);
-        // this thread's elements of the window, in registers for every round
-        float v[E], out[E];
-        if (vec) {
+    // this thread's elements of a window (the window after the current one is fetched while the current one is
+    // scanned: with hundreds of frames in flight the array comes from HBM, not from L2)
+    auto load_win = [&](int wb, float (&dst)[E]) {
+        const int jj = wb + tid * E;
+        if ((jj + E <= N) && ((reinterpret_cast<unsigned long long>(a + jj) & 15ull) == 0ull)) {
 #pragma unroll
             for (int q = 0; q < E / 4; ++q) {
-                const float4 t = *reinterpret_cast<const float4 *>(a + j0 + 4 * q);
-                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                const float4 t = *reinterpret_cast<const float4 *>(a + jj + 4 * q);
+                dst[4 * q] = t.x; dst[4 * q + 1] = t.y; dst[4 * q + 2] = t.z; dst[4 * q + 3] = t.w;
             }
         } else {
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[e] = (j0 + e < N) ? a[j0 + e] : 0.0f;
+            for (int e = 0; e < E; ++e) dst[e] = (jj + e < N) ? a[jj + e] : 0.0f;
         }
+    };
+    float vnext[E];
+    load_win(0, vnext);
+    for (int wbase = 0; wbase < N; wbase += GSC_SCAN_WIN) {
+        const int wend = min(N, wbase + GSC_SCAN_WIN);
+        const int j0 = wbase + tid * E;
+        const bool vec = (j0 + E <= N) && ((reinterpret_cast<unsigned long long>(r + j0) & 15ull) == 0ull);
+        // this thread's elements of the window, in registers for every round
+        float v[E], out[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = vnext[e];
+        if (wbase + GSC_SCAN_WIN < N) load_win(wbase + GSC_SCAN_WIN, vnext);
 #pragma unroll
         for (int e = 0; e < E; ++e) out[e] = 0.0f;
         for (;;) {   // rounds

@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                 const int cnt = __popc(hit);
                 int hotT = 1;
                 {
-                    constexpr int CH = 170, CT = 450;
+                    constexpr int CH = 300, CT = 450;
                     const int wmax = (int)__reduce_max_sync(FULL, (unsigned)cnt);
                     int bestc = 0x7fffffff;
                     const int opts[8] = {1, 3, 5, 7, 9, 13, 17, 33};
