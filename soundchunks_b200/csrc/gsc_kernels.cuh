@@ -519,10 +519,13 @@ __global__ void __launch_bounds__(GSC_SEED_THREADS) k_seed(const GscFrame *__res
         }
         __syncthreads();
         if (tid == 0) { const unsigned long long t1 = clock64(); c_pick += t1 - c_t; c_t = t1; }
-        float c[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) c[k] = s_c[k];
         const float cn = s_cn;
+        // the seed row stays in shared memory and is re-read where a row is actually scored (~5 % of the points):
+        // the registers it would occupy pay for the prefetch of the next quad below
+        auto seed_row = [&](float (&c)[D]) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) c[k] = *reinterpret_cast<const volatile float *>(&s_c[k]);
+        };
         // A point's row is only fetched when the new seed can lower its distance: the reverse triangle
         // inequality gives d >= (|p| - |c|)^2, and yakmo's float evaluation of d stays within a few ulps of
         // (cn + pn) of the true value; the margins below cover both, so `up[j] > d` is false for every skipped
@@ -531,8 +534,9 @@ __global__ void __launch_bounds__(GSC_SEED_THREADS) k_seed(const GscFrame *__res
         const float mrg = 4e-6f;
         if (i == 0) {
             for (int j = tid; j < N; j += blockDim.x) {
-                float p[D];
+                float p[D], c[D];
                 gsc_load_row<D>(Xf, j, p);
+                seed_row(c);
                 upf[j] = gsc_yakmo_dist<D>(p, pn[j], c, cn);
                 sidf[j] = 0;
             }
@@ -540,18 +544,23 @@ __global__ void __launch_bounds__(GSC_SEED_THREADS) k_seed(const GscFrame *__res
             // 4 consecutive points per thread and step: two 128-bit loads (norms, current distances) decide
             const bool al = ((reinterpret_cast<unsigned long long>(pn) | reinterpret_cast<unsigned long long>(upf)) & 15ull) == 0ull;
             const int N4 = al ? (N & ~3) : 0;
-#pragma unroll 2
-            for (int j4 = tid * 4; j4 < N4; j4 += blockDim.x * 4) {
-                const float4 pq = *reinterpret_cast<const float4 *>(pn + j4);
-                const float4 uq = *reinterpret_cast<const float4 *>(upf + j4);
+            // the loads of the next quad are issued before this one is processed (the stores to up[] below would
+            // otherwise keep the compiler from overlapping them; a thread only ever touches its own quads)
+            const int st4 = blockDim.x * 4;
+            float4 pqn = make_float4(0.f, 0.f, 0.f, 0.f), uqn = pqn;
+            if (tid * 4 < N4) { pqn = *reinterpret_cast<const float4 *>(pn + tid * 4); uqn = *reinterpret_cast<const float4 *>(upf + tid * 4); }
+            for (int j4 = tid * 4; j4 < N4; j4 += st4) {
+                const float4 pq = pqn, uq = uqn;
+                if (j4 + st4 < N4) { pqn = *reinterpret_cast<const float4 *>(pn + j4 + st4); uqn = *reinterpret_cast<const float4 *>(upf + j4 + st4); }
                 const float pjs[4] = {pq.x, pq.y, pq.z, pq.w}, ujs[4] = {uq.x, uq.y, uq.z, uq.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float t = sqrtf(pjs[q]) - scn;
                     const float lb = t * t * (1.0f - mrg) - mrg * (cn + pjs[q]) - 1e-37f;
                     if (!(lb > ujs[q])) {          // the seed may lower this distance: fetch the row
-                        float p[D];
+                        float p[D], c[D];
                         gsc_load_row<D>(Xf, j4 + q, p);
+                        seed_row(c);
                         const float d = gsc_yakmo_dist<D>(p, pjs[q], c, cn);
                         if (ujs[q] > d) { upf[j4 + q] = d; sidf[j4 + q] = i; }
                     }
@@ -562,8 +571,9 @@ __global__ void __launch_bounds__(GSC_SEED_THREADS) k_seed(const GscFrame *__res
                 const float t = sqrtf(pj) - scn;
                 const float lb = t * t * (1.0f - mrg) - mrg * (cn + pj) - 1e-37f;
                 if (lb > uj) continue;
-                float p[D];
+                float p[D], c[D];
                 gsc_load_row<D>(Xf, j, p);
+                seed_row(c);
                 const float d = gsc_yakmo_dist<D>(p, pj, c, cn);
                 if (uj > d) { upf[j] = d; sidf[j] = i; }
             }
