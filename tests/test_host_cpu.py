@@ -49,6 +49,19 @@ def test_libgsc_host_exports_every_declared_symbol(host):
         assert getattr(lib, n) is not None, n
 
 
+def test_build_rejects_spilling_online_shapes():
+    """build.py treats a k_online shape that ptxas compiled with register spills as a build error."""
+    from soundchunks_b200.build import online_spills
+    log = ("ptxas info    : Compiling entry function '_Z8k_onlineILi8ELi16ELi256EEvPK8GscFrame' for 'sm_100a'\n"
+           "ptxas info    : Function properties for _Z8k_onlineILi8ELi16ELi256EEvPK8GscFrame\n"
+           "    24 bytes stack frame, 36 bytes spill stores, 32 bytes spill loads\n"
+           "ptxas info    : Compiling entry function '_Z8k_onlineILi8ELi8ELi128EEvPK8GscFrame' for 'sm_100a'\n"
+           "    0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads\n"
+           "ptxas info    : Compiling entry function '_Z6k_seedILi8EEvPK8GscFrame' for 'sm_100a'\n"
+           "    104 bytes stack frame, 172 bytes spill stores, 152 bytes spill loads\n")
+    assert online_spills(log) == ["_Z8k_onlineILi8ELi16ELi256EEvPK8GscFrame"]
+
+
 def test_no_gpu_fails_loudly(lib_built):
     """Without a usable sm_100 device every entry point must fail with a message, never compute on the CPU."""
     import soundchunks_b200 as sc
