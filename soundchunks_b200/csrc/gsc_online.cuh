@@ -395,15 +395,16 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const unsigned dirty = (unsigned)gsc_lds_i(sb + Ly::DIRTY + 4u * cell);
                     if (dirty) {
                         gsc_sts_i(sb + Ly::DIRTY + 4u * cell, 0);
+                        // pair-wise: both centroids of a touched register pair are re-read (filter dimensions only),
+                        // h_c comes from the H table the resolver keeps (same formula)
 #pragma unroll
-                        for (int j = 0; j < CPT; ++j)
-                            if (dirty & (1u << j)) {
-                                float r[D];
-                                gsc_lds_row<D>(sb + Ly::C + (unsigned)(first + j) * D * 4, r);
-                                float nc = 0.0f;
-#pragma unroll
-                                for (int k = 0; k < DF; ++k) nc = fmaf(r[k], r[k], nc);
-                                gsc_filter_set<CPT, DF>(fcp, hp, j, r, -0.5f * nc * (1.0f - GSC_ON_G));
+                        for (int p2 = 0; p2 < CPT / 2; ++p2)
+                            if (dirty & (3u << (2 * p2))) {
+                                const float4 ra = gsc_lds_f4(sb + Ly::C + (unsigned)(first + 2 * p2) * D * 4);
+                                const float4 rb = gsc_lds_f4(sb + Ly::C + (unsigned)(first + 2 * p2 + 1) * D * 4);
+                                fcp[p2][0] = gsc_pk2(ra.x, rb.x); fcp[p2][1] = gsc_pk2(ra.y, rb.y);
+                                fcp[p2][2] = gsc_pk2(ra.z, rb.z); fcp[p2][3] = gsc_pk2(ra.w, rb.w);
+                                hp[p2] = gsc_lds_u64(sb + Ly::H + (unsigned)(first + 2 * p2) * 4u);
                             }
                         c0lo = INFINITY; c0hi = -INFINITY;
 #pragma unroll
