@@ -273,6 +273,10 @@ int gsc_debug_online_counters(gsc_ctx *ctx, unsigned long long *out, int n_frame
  * distance pass, prefix scan, number of steps. */
 int gsc_debug_seed_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
 
+/* The library's natural logarithm (csrc/gsc_log.h: correctly rounded, plain IEEE double operations; the cepstral
+ * features enc:316-318 go through it) over a host array, so that a host can compare it value by value. */
+int gsc_log_array(gsc_ctx *ctx, const double *x, int64_t n, double *y);
+
 /* FP32 FFMA throughput probe (roofline denominator for the k-means / search
  * kernels): returns measured TFLOP/s on the context's device. */
 int gsc_fp32_peak_probe(gsc_ctx *ctx, double *tflops);

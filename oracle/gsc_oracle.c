@@ -18,6 +18,9 @@
  *   math.log10(x)      ln(x) * 0.43429448190325182765
  */
 #include "gsc_oracle.h"
+/* the one routine shared with the product: a correctly-rounded ln in plain IEEE double operations, so that the
+ * cepstral features do not depend on whose libm evaluated log() (checked against mpmath, tests/test_log_cr.py) */
+#include "../soundchunks_b200/csrc/gsc_log.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -31,6 +34,8 @@
 /* ------------------------------------------------------------------ */
 /* scalar sample functions                                            */
 /* ------------------------------------------------------------------ */
+
+double gsc_ref_log_cr(double x) { return gsc_log_cr(x); }
 
 /* enc:1643-1646 */
 double gsc_ref_float_sample(int16_t s) { return (double)s / 32767.0; }
@@ -172,7 +177,7 @@ static void chunk_features_t(const trig_tables *t, const double *x, int neg,
     }
     for (int i = 0; i < cs; ++i)                                   /* enc:316-318 */
         if (!(fabs(temp[i]) <= 1e-12))
-            temp[i] = log(temp[i]) * 0.43429448190325182765;
+            temp[i] = gsc_log_cr(temp[i]) * 0.43429448190325182765;
     for (int k = 0; k < cs; ++k) {                                 /* enc:280-302 */
         double re = 0, im = 0;
         for (int i = 0; i < cs; ++i) {
@@ -818,6 +823,8 @@ void gsc_ref_default_params(gsc_ref_params *p)
     p->batch = 512;
     p->frame_length_ms = 4000.0;
     p->vfr = 1.0;
+    p->band_all = 0;
+    p->reserved = 0;
 }
 
 int gsc_ref_encode_frame(const int16_t *pcm, int64_t stride, int C, int S,
@@ -869,7 +876,14 @@ int gsc_ref_encode_frame(const int16_t *pcm, int64_t stride, int C, int S,
     int32_t *best = (int32_t *)malloc(sizeof(int32_t) * N);
     int32_t *use = (int32_t *)malloc(sizeof(int32_t) * R);
     int32_t *band = (int32_t *)malloc(sizeof(int32_t) * N);
-    gsc_ref_knnfit(dict, datten, R, cs, bits, divider, raw, N, best, use, band, NULL, NULL);
+    if (p->band_all) {
+        int32_t *b64 = (int32_t *)malloc(sizeof(int32_t) * N);
+        gsc_ref_knnfit(dict, datten, R, cs, bits, divider, raw, N, b64, NULL, band, best, NULL);
+        memset(use, 0, sizeof(int32_t) * R);
+        for (int j = 0; j < N; ++j) use[best[j] >> 2]++;
+        free(b64);
+    } else
+        gsc_ref_knnfit(dict, datten, R, cs, bits, divider, raw, N, best, use, band, NULL, NULL);
     int32_t *remap = (int32_t *)malloc(sizeof(int32_t) * R);
     int32_t *norder = (int32_t *)malloc(sizeof(int32_t) * R);
     int R2 = gsc_ref_finalize_dictionary(use, R, remap, norder);

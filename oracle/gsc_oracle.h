@@ -35,6 +35,7 @@ extern "C" {
 #endif
 
 /* ---- scalar sample functions (enc:1638-1698) ---- */
+double  gsc_ref_log_cr(double x);   /* the shared correctly-rounded ln (soundchunks_b200/csrc/gsc_log.h) */
 double  gsc_ref_float_sample(int16_t s);
 int16_t gsc_ref_make16(double smp);
 int16_t gsc_ref_quant(double smp, int bits, int atten, int neg, double law);
@@ -147,6 +148,11 @@ typedef struct gsc_ref_params {
     int batch;             /* mode 2 */
     double frame_length_ms;/* -fl  default 4000  enc:1501 */
     double vfr;            /* -vfr default 1.0   enc:1499 */
+    int band_all;          /* KNNFit band rule: 0 = among the 64 nearest rows (ANN's bucket, enc:917,952;
+                              ties in index order where ANN's visit order is not reproducible),
+                              1 = among ALL rows inside the epsilon band (what libgsc_cuda computes; the
+                              two agree whenever overfull == 0) */
+    int reserved;
 } gsc_ref_params;
 
 void gsc_ref_default_params(gsc_ref_params *p);

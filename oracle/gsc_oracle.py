@@ -34,7 +34,8 @@ class _Params(C.Structure):
                 ("chunks_per_frame", C.c_int), ("precision", C.c_int),
                 ("max_passes", C.c_int), ("kmeans_mode", C.c_int),
                 ("lloyd_iters", C.c_int), ("batch", C.c_int),
-                ("frame_length_ms", C.c_double), ("vfr", C.c_double)]
+                ("frame_length_ms", C.c_double), ("vfr", C.c_double),
+                ("band_all", C.c_int), ("reserved", C.c_int)]
 
 
 class _FrameOut(C.Structure):
@@ -71,6 +72,8 @@ def lib():
     if _lib is None:
         build()
         L = C.CDLL(_SO)
+        L.gsc_ref_log_cr.restype = C.c_double
+        L.gsc_ref_log_cr.argtypes = [C.c_double]
         L.gsc_ref_float_sample.restype = C.c_double
         L.gsc_ref_float_sample.argtypes = [C.c_int16]
         L.gsc_ref_make16.restype = C.c_int16

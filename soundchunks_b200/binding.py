@@ -14,7 +14,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgsc_cuda.so")
+# GSC_CUDA_SO: load another build of the same library (tools/spill_probe.py uses register-capped debug builds)
+SO_PATH = os.environ.get("GSC_CUDA_SO") or os.path.join(_HERE, "libgsc_cuda.so")
 
 #: every symbol include/gsc_cuda.h declares (checked by the CPU test-suite)
 EXPORTS = [
@@ -26,7 +27,7 @@ EXPORTS = [
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
     "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters", "gsc_debug_seed_counters",
+    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters", "gsc_debug_seed_counters",
 ]
 
 
@@ -203,6 +204,12 @@ class Context:
         self._ck(self.L.gsc_debug_seed_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
 
+    def log_array(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        self._ck(self.L.gsc_log_array(C.c_void_p(self.h), _vp(x), C.c_int64(x.size), _vp(y)))
+        return y
+
     def fp32_peak_tflops(self) -> float:
         v = C.c_double(0)
         self._ck(self.L.gsc_fp32_peak_probe(C.c_void_p(self.h), C.byref(v)))
@@ -360,8 +367,9 @@ class Context:
         """.gsc bytes of the last batch, packed on the device -> (bytes, per-frame sizes)."""
         sizes = np.zeros(n_frames, np.int64)
         total = C.c_int64(0)
+        # sizing call: packs on the device and brings back 8 bytes per frame; the second call copies the bytes (once)
         self._ck(self.L.gsc_fetch_stream(C.c_void_p(self.h), n_frames, sample_rate, None, C.c_int64(0), _vp(sizes), C.byref(total)))
-        out = np.zeros(max(total.value, 1), np.uint8)
+        out = np.empty(max(total.value, 1), np.uint8)
         self._ck(self.L.gsc_fetch_stream(C.c_void_p(self.h), n_frames, sample_rate, _vp(out), C.c_int64(total.value), _vp(sizes), C.byref(total)))
         return out[:total.value].tobytes(), sizes
 

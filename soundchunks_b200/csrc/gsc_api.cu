@@ -129,6 +129,11 @@ struct gsc_ctx {
     bool split = false;
     std::vector<int> idx_a, idx_b;   // frames of the last split batch handled by this context / by the peer
     double stage_t[8] = {};          // start of stage i (ev[i]) in ms after the batch's fork event, filled at fetch
+    // .gsc stream of the last batch: packed once (k_pack_frames), sizes kept for the second gsc_fetch_stream call
+    bool packed = false;
+    std::vector<long long> pk_sizes;  // bytes per frame of this lane
+    DevBuf scompact, soffs;           // main context: the batch's frames back to back in frame order; per-lane offsets
+    HostBuf hsizes;
 };
 
 static std::atomic<int> g_rr{0};
@@ -190,8 +195,9 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
-                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr};
+                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr, &c->scompact, &c->soffs};
     for (DevBuf *b : bufs) b->release();
+    c->hsizes.release();
     c->hpcm.release();
     c->hout.release();
     c->hstream.release();
@@ -307,7 +313,15 @@ static int plan_batch(gsc_ctx *c, const gsc_frame_desc *fr, int F, int cs, int K
         if (g.N > maxN) maxN = g.N;
     }
     c->F = F; c->sumN = off; c->maxN = maxN; c->Kmax = K; c->cs = cs; c->pcm_samples = pcm_off;
+    c->packed = false;
     return GSC_OK;
+}
+
+// The single-frame stage calls re-plan the context: whatever a previous gsc_encode_frames batch left behind
+// (lane split, packed stream) no longer describes the buffers.
+static void forget_batch(gsc_ctx *c) {
+    c->split = false; c->idx_a.clear(); c->idx_b.clear(); c->packed = false;
+    if (c->peer) c->peer->packed = false;
 }
 
 static int upload_frames(gsc_ctx *c) {
@@ -602,6 +616,7 @@ static int single_frame_pcm(gsc_ctx *c, const int16_t *pcm, int64_t stride, int 
     if (!pcm || C <= 0 || S <= 0) return set_err(GSC_ERR_ARG, "bad pcm arguments");
     gsc_frame_desc d = {pcm, stride, C, S};
     c->bits = bits;
+    forget_batch(c);
     TRY(plan_batch(c, &d, 1, cs, K, precision, true, nullptr));
     TRY(c->hpcm.ensure(2 * (size_t)C * S));
     for (int j = 0; j < C; ++j) memcpy(c->hpcm.as<int16_t>() + (size_t)j * S, pcm + (size_t)j * stride, 2 * (size_t)S);
@@ -612,6 +627,7 @@ static int single_frame_pcm(gsc_ctx *c, const int16_t *pcm, int64_t stride, int 
 
 // One-frame batch for feature-space calls (no PCM).
 static int single_frame_points(gsc_ctx *c, int N, int K) {
+    forget_batch(c);
     c->h_frames.resize(1);
     GscFrame &g = c->h_frames[0];
     memset(&g, 0, sizeof(g));
@@ -1048,23 +1064,22 @@ static long long stream_cap(const gsc_ctx *c) {   // bytes per frame slot, multi
     const long long v = 12 + (c->Kmax + 1) / 2 + 2LL * c->Kmax * c->cs + 4 + 2 * ((17LL * c->maxN + 15) / 16) + 8;
     return (v + 3) & ~3LL;
 }
-// pack the .gsc bytes of one lane's frames into c->sbytes, sizes into c->snb, and bring both to the host
-static int pack_one(gsc_ctx *c, int sample_rate, std::vector<long long> &nb, const unsigned char **bytes, long long *cap_out) {
+// k_pack_frames for one lane's frames (once per batch) + its per-frame sizes on the host
+static int pack_lane(gsc_ctx *c, int sample_rate) {
     CU(cudaSetDevice(c->device));
     const long long cap = stream_cap(c);
-    TRY(c->sbytes.ensure((size_t)cap * c->F)); TRY(c->snb.ensure(8 * (size_t)c->F));
-    DISPATCH_CS(c->cs, LAUNCH(c, k_pack_frames<CS>, c->F, 1024, 0, c->frames.as<GscFrame>(), c->bits, sample_rate,
-                              c->divider.as<int>(), c->newR.as<int>(), c->odict.as<short>(), c->odatten.as<unsigned char>(),
-                              c->oindex.as<int>(), c->oattr.as<unsigned char>(), c->sbytes.as<unsigned char>(), cap,
-                              c->snb.as<long long>(), c->Kmax));
-    nb.resize(c->F);
-    TRY(c->hstream.ensure((size_t)cap * c->F));
-    TRY(d2h(c, nb.data(), c->snb.p, 8 * (size_t)c->F));   // pageable destination: returns when the sizes are there
-    for (int i = 0; i < c->F; ++i)                          // only the bytes each frame uses
-        TRY(d2h(c, c->hstream.as<unsigned char>() + (size_t)cap * i, c->sbytes.as<unsigned char>() + (size_t)cap * i, (size_t)nb[i]));
-    TRY(sync(c));
-    *bytes = c->hstream.as<unsigned char>();
-    *cap_out = cap;
+    if (!c->packed) {
+        TRY(c->sbytes.ensure((size_t)cap * c->F)); TRY(c->snb.ensure(8 * (size_t)c->F));
+        DISPATCH_CS(c->cs, LAUNCH(c, k_pack_frames<CS>, c->F, 1024, 0, c->frames.as<GscFrame>(), c->bits, sample_rate,
+                                  c->divider.as<int>(), c->newR.as<int>(), c->odict.as<short>(), c->odatten.as<unsigned char>(),
+                                  c->oindex.as<int>(), c->oattr.as<unsigned char>(), c->sbytes.as<unsigned char>(), cap,
+                                  c->snb.as<long long>(), c->Kmax));
+        TRY(c->hsizes.ensure(8 * (size_t)c->F));
+        TRY(d2h(c, c->hsizes.p, c->snb.p, 8 * (size_t)c->F));
+        TRY(sync(c));                                        // the sizes are read on the host right below
+        c->pk_sizes.assign(c->hsizes.as<long long>(), c->hsizes.as<long long>() + c->F);
+        c->packed = true;
+    }
     return GSC_OK;
 }
 
@@ -1074,27 +1089,41 @@ extern "C" int gsc_fetch_stream(gsc_ctx *c, int n_frames, int sample_rate, uint8
     if (!c || n_frames <= 0 || sample_rate <= 0 || sample_rate >= (1 << 24)) return set_err(GSC_ERR_ARG, "bad arguments to gsc_fetch_stream");
     const bool split = c->split && c->peer;
     if (n_frames != (split ? (int)(c->idx_a.size() + c->idx_b.size()) : c->F)) return set_err(GSC_ERR_ARG, "gsc_fetch_stream: frame count does not match the last batch");
-    std::vector<long long> na, nbv;
-    const unsigned char *ba = nullptr, *bb = nullptr;
-    long long ca = 0, cb = 0;
-    TRY(pack_one(c, sample_rate, na, &ba, &ca));
-    if (split) TRY(pack_one(c->peer, sample_rate, nbv, &bb, &cb));
+    // pack each lane once per batch (a sizing call and the fetch that follows share the result)
+    TRY(pack_lane(c, sample_rate));
+    if (split) TRY(pack_lane(c->peer, sample_rate));
     long long sum = 0;
-    std::vector<long long> sz(n_frames);
-    for (int i = 0; i < n_frames; ++i) {
-        sz[i] = split ? ((i & 1) ? nbv[i >> 1] : na[i >> 1]) : na[i];
-        sum += sz[i];
+    std::vector<long long> off(n_frames);
+    for (int i = 0; i < n_frames; ++i) {                    // frames in index order (enc:1208-1214)
+        const long long sz = split ? ((i & 1) ? c->peer->pk_sizes[i >> 1] : c->pk_sizes[i >> 1]) : c->pk_sizes[i];
+        off[i] = sum;
+        sum += sz;
+        if (frame_bytes) frame_bytes[i] = sz;
     }
     if (total) *total = sum;
-    if (frame_bytes) for (int i = 0; i < n_frames; ++i) frame_bytes[i] = sz[i];
-    if (!out) return GSC_OK;                      // sizing call
+    if (!out) return GSC_OK;                                // sizing call: nothing but the sizes came back
     if (cap < sum) return set_err(GSC_ERR_ARG, "gsc_fetch_stream: %lld bytes needed, room for %lld", sum, (long long)cap);
-    long long off = 0;
-    for (int i = 0; i < n_frames; ++i) {          // frames in index order (enc:1208-1214)
-        const unsigned char *src = split ? ((i & 1) ? bb + (long long)(i >> 1) * cb : ba + (long long)(i >> 1) * ca) : ba + (long long)i * ca;
-        memcpy(out + off, src, (size_t)sz[i]);
-        off += sz[i];
+    // compact on the device into frame order, then ONE device-to-host copy of exactly the stream's bytes
+    CU(cudaSetDevice(c->device));
+    TRY(c->scompact.ensure((size_t)sum + 16));
+    std::vector<long long> lo[2];                           // alive until the final synchronisation below
+    for (int lane = 0; lane < (split ? 2 : 1); ++lane) {
+        gsc_ctx *l = lane ? c->peer : c;
+        lo[lane].resize(l->F);
+        for (int k = 0; k < l->F; ++k) lo[lane][k] = off[split ? 2 * k + lane : k];
+        TRY(l->soffs.ensure(8 * (size_t)l->F));
+        TRY(h2d(l, l->soffs.p, lo[lane].data(), 8 * (size_t)l->F));
+        LAUNCH(l, k_compact_stream, l->F, 256, 0, l->sbytes.as<unsigned char>(), stream_cap(l), l->snb.as<long long>(),
+               l->soffs.as<long long>(), c->scompact.as<unsigned char>());
+        if (lane) {                                         // join: the copy below waits for the second lane's frames
+            CU(cudaEventRecord(l->ev[8], l->stream));
+            CU(cudaStreamWaitEvent(c->stream, l->ev[8], 0));
+        }
     }
+    TRY(c->hstream.ensure((size_t)sum));
+    TRY(d2h(c, c->hstream.p, c->scompact.p, (size_t)sum));
+    TRY(sync(c));
+    memcpy(out, c->hstream.p, (size_t)sum);
     return GSC_OK;
 }
 
@@ -1163,8 +1192,15 @@ static int launch_lanes(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, 
     CU(cudaSetDevice(c->device));
     CU(cudaEventRecord(c->ev[8], c->stream));
     CU(cudaStreamWaitEvent(c->peer->stream, c->ev[8], 0));
-    TRY(launch(c, fa.data(), (int)fa.size(), P));
-    TRY(launch(c->peer, fb.data(), (int)fb.size(), P));
+    int rc = launch(c, fa.data(), (int)fa.size(), P);
+    if (rc == GSC_OK) rc = launch(c->peer, fb.data(), (int)fb.size(), P);
+    if (rc != GSC_OK) {   // leave no half-planned batch behind: drain both lanes, forget the split
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->peer->stream);
+        cudaGetLastError();
+        forget_batch(c);
+        return rc;
+    }
     CU(cudaEventRecord(c->peer->ev[8], c->peer->stream));
     CU(cudaStreamWaitEvent(c->stream, c->peer->ev[8], 0));
     return GSC_OK;
@@ -1230,6 +1266,19 @@ extern "C" int gsc_encode_frames_dev(gsc_ctx *c, const gsc_frame_desc *frames, i
     if (!c || !frames || n_frames <= 0) return set_err(GSC_ERR_ARG, "bad arguments to gsc_encode_frames_dev");
     TRY(check_params(P));
     return launch_lanes(c, frames, n_frames, P, launch_dev);
+}
+
+// gsc_log_cr (csrc/gsc_log.h) over a host array: lets a host check the library's logarithm value by value.
+extern "C" int gsc_log_array(gsc_ctx *c, const double *x, int64_t n, double *y) {
+    FpGuard g;
+    if (!c || !x || !y || n <= 0) return set_err(GSC_ERR_ARG, "bad arguments to gsc_log_array");
+    CU(cudaSetDevice(c->device));
+    TRY(c->misc.ensure(16 * (size_t)n));
+    double *dx = c->misc.as<double>(), *dy = dx + n;
+    TRY(h2d(c, dx, x, 8 * (size_t)n));
+    LAUNCH(c, k_log_array, (unsigned)((n + 255) / 256), 256, 0, dx, dy, (long long)n);
+    TRY(d2h(c, y, dy, 8 * (size_t)n));
+    return sync(c);
 }
 
 extern "C" int gsc_fp32_peak_probe(gsc_ctx *c, double *tflops) {

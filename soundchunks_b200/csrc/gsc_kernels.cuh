@@ -12,6 +12,7 @@
 //   Lloyd: k_assign (+ k_owner_sums) ; legacy ANN: k_ann_*
 #pragma once
 #include "gsc_device.cuh"
+#include "gsc_log.h"
 
 // ---------------------------------------------------------------------------
 // Constant tables: trig tables are computed on the HOST with libm so that
@@ -115,8 +116,8 @@ __device__ __forceinline__ void gsc_features(const double (&x)[CS], bool neg, bo
         temp[k] = re * re + im * im;
     }
 #pragma unroll
-    for (int i = 0; i < CS; ++i)  // enc:316-318, math.log10 = ln(x)*const
-        if (!(fabs(temp[i]) <= 1e-12)) temp[i] = log(temp[i]) * 0.43429448190325182765;
+    for (int i = 0; i < CS; ++i)  // enc:316-318, math.log10 = ln(x)*const; ln = the shared correctly-rounded routine
+        if (!(fabs(temp[i]) <= 1e-12)) temp[i] = gsc_log_cr(temp[i]) * 0.43429448190325182765;
 #pragma unroll
     for (int k = 0; k < CS; ++k) {  // enc:280-302 iDFT magnitude
         double re = 0, im = 0;
@@ -1349,6 +1350,31 @@ __global__ void __launch_bounds__(1024) k_pack_frames(const GscFrame *__restrict
     }
 }
 
+// The packed frames, each in its own `cap`-byte slot, copied back to back to their offsets in the batch's stream
+// (frame order, enc:1208-1214): one CTA per frame, 16-byte loads where the destination allows.
+__global__ void __launch_bounds__(256) k_compact_stream(const unsigned char *__restrict__ src, long long cap,
+                                                        const long long *__restrict__ nbytes,
+                                                        const long long *__restrict__ offs,
+                                                        unsigned char *__restrict__ dst) {
+    const long long n = nbytes[blockIdx.x];
+    const unsigned char *s = src + (long long)blockIdx.x * cap;
+    unsigned char *d = dst + offs[blockIdx.x];
+    const long long head = min(n, (long long)((16 - (reinterpret_cast<unsigned long long>(d) & 15ull)) & 15ull));
+    for (long long i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+    const long long body = (n - head) / 16;
+    // the source of the body is not 16-byte aligned in general: assemble from 4-byte words (cap is a multiple of 4
+    // and so is every frame's start; head shifts the phase by at most 15 bytes)
+    for (long long i = threadIdx.x; i < body; i += blockDim.x) {
+        const unsigned char *p = s + head + 16 * i;
+        uint4 v;
+        unsigned char *vb = reinterpret_cast<unsigned char *>(&v);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) vb[k] = p[k];
+        *reinterpret_cast<uint4 *>(d + head + 16 * i) = v;
+    }
+    for (long long i = head + 16 * body + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+}
+
 // encoder-side reconstruction (enc:487-522, 1518-1582) and the squared error behind PsyADelta
 // (enc:1862-1880).  One thread per chunk; the error sum is a sum of squared int16 differences, exact in 64-bit
 // integers, so sqrt(sum / count) in Double equals the reference's sequential Double sum bit for bit.
@@ -1624,6 +1650,12 @@ __global__ void __launch_bounds__(256) k_ann_query(const float *__restrict__ pts
         }
         __syncthreads();
     }
+}
+
+// gsc_log_cr over an array (gsc_log_array: lets a host check the library's logarithm value by value).
+__global__ void k_log_array(const double *__restrict__ x, double *__restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = gsc_log_cr(x[i]);
 }
 
 // FP32 FFMA throughput probe (roofline denominator).

@@ -200,12 +200,12 @@ struct GscOnLayout {
     static constexpr unsigned G = HX + GSC_ON_TP * 4;                 // int   [TP]
     static constexpr unsigned LIST = G + GSC_ON_TP * 4;               // u64   [L][B] (slot-major)
     static constexpr unsigned LISTN = LIST + GSC_ON_B * GSC_ON_L * 8; // int   [B] entries per point (may exceed L: overflow)
-    // thresholds and slabs of the batch: every warp computes and writes the same 32 values (benign: identical
-    // data) and reads them after its own __syncwarp, so one copy serves all warps without a block barrier
-    static constexpr unsigned THRW = LISTN + GSC_ON_B * 4;            // float [B] candidate thresholds
-    static constexpr unsigned XLO = THRW + GSC_ON_B * 4;              // float [B] slab x0 - r
-    static constexpr unsigned XHI = XLO + GSC_ON_B * 4;               // float [B] slab x0 + r
-    static constexpr unsigned MOVED = XHI + GSC_ON_B * 4;             // int   [B]
+    // thresholds and slabs of the batch: every warp computes the same 32 values and keeps its OWN copy (written
+    // and read behind the warp's own __syncwarp, no block barrier and no cross-warp sharing)
+    static constexpr unsigned THRW = LISTN + GSC_ON_B * 4;            // float [W][B] candidate thresholds
+    static constexpr unsigned XLO = THRW + (T / 32) * GSC_ON_B * 4;   // float [W][B] slab x0 - r
+    static constexpr unsigned XHI = XLO + (T / 32) * GSC_ON_B * 4;    // float [W][B] slab x0 + r
+    static constexpr unsigned MOVED = XHI + (T / 32) * GSC_ON_B * 4;  // int   [B] distinct centroids moved in this batch
     static constexpr unsigned ROWS = MOVED + GSC_ON_B * 4;            // float [B][D]
     static constexpr unsigned WS = ROWS + GSC_ON_B * D * 4;           // int   [B]
     static constexpr unsigned ETB = WS + GSC_ON_B * 4;                // float [2][B]
@@ -232,8 +232,15 @@ struct GscOnLayout {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget of one SM");
 };
 
+// GSC_ONLINE_MAXNREG (debug builds of tools/spill_probe.py only): cap the registers below what the kernel needs, so
+// that ptxas spills -- the results must not change.
+#ifdef GSC_ONLINE_MAXNREG
+#define GSC_ONLINE_BOUNDS(T) __maxnreg__(GSC_ONLINE_MAXNREG)
+#else
+#define GSC_ONLINE_BOUNDS(T) __launch_bounds__(T)
+#endif
 template <int D, int CPT, int T>
-__global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frames,
+__global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frames,
                                               const float *__restrict__ X,       // [sumN][D]
                                               float *__restrict__ cen,           // [F][Kmax][D] in/out
                                               int *__restrict__ labels,          // [sumN] in: guesses, out: labels
@@ -262,6 +269,10 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
     // and this spreads them over all warps.
     const int cell = lane * (T / 32) + warp;
     const int first = cell * CPT;
+    // this warp's copy of the batch thresholds / slabs
+    const unsigned thrw = sb + Ly::THRW + (unsigned)warp * (GSC_ON_B * 4u);
+    const unsigned xlo = sb + Ly::XLO + (unsigned)warp * (GSC_ON_B * 4u);
+    const unsigned xhi = sb + Ly::XHI + (unsigned)warp * (GSC_ON_B * 4u);
     const float *Xf = X + f.chunk_off * D;
     int *lab = labels + f.chunk_off;
     float *cf = cen + (long long)f.slot * Kmax * D;
@@ -433,17 +444,17 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const bool on = lane < nb && !force_exact;
                     // slab half-width: sqrt(U) widened for every rounding of the test and of the exact distance
                     const float rr = sqrtf(Umine) * 1.000002f + 4.0e-7f * fabsf(xb[0]) + 1e-30f;
-                    gsc_sts_f(sb + Ly::THRW + (unsigned)lane * 4u, on ? gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * Umine : INFINITY);
-                    gsc_sts_f(sb + Ly::XLO + (unsigned)lane * 4u, on ? xb[0] - rr : INFINITY);
-                    gsc_sts_f(sb + Ly::XHI + (unsigned)lane * 4u, on ? xb[0] + rr : -INFINITY);
+                    gsc_sts_f(thrw + (unsigned)lane * 4u, on ? gsc_lds_f(sb + Ly::HX + 4u * (pos + lane)) - 0.5f * Umine : INFINITY);
+                    gsc_sts_f(xlo + (unsigned)lane * 4u, on ? xb[0] - rr : INFINITY);
+                    gsc_sts_f(xhi + (unsigned)lane * 4u, on ? xb[0] + rr : -INFINITY);
                 }
                 __syncwarp();
                 // pass (a): which points' slabs meet this thread's c0 range (one bit per point, branch-free)
                 unsigned hit = 0;
 #pragma unroll
                 for (int b4 = 0; b4 < B; b4 += 4) {
-                    const float4 xl = gsc_lds_f4(sb + Ly::XLO + (unsigned)b4 * 4u);
-                    const float4 xh = gsc_lds_f4(sb + Ly::XHI + (unsigned)b4 * 4u);
+                    const float4 xl = gsc_lds_f4(xlo + (unsigned)b4 * 4u);
+                    const float4 xh = gsc_lds_f4(xhi + (unsigned)b4 * 4u);
                     hit |= ((xh.x >= c0lo) && (xl.x <= c0hi)) ? (1u << b4) : 0u;
                     hit |= ((xh.y >= c0lo) && (xl.y <= c0hi)) ? (2u << b4) : 0u;
                     hit |= ((xh.z >= c0lo) && (xl.z <= c0hi)) ? (4u << b4) : 0u;
@@ -505,7 +516,7 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const int o = __ffs(hm) - 1;
                     const unsigned ho = __shfl_sync(FULL, hit, o);
                     const int fo = (o * W + warp) * CPT;   // first slot of the owner's cell
-                    const float thr = gsc_lds_f(sb + Ly::THRW + (unsigned)lane * 4u);
+                    const float thr = gsc_lds_f(thrw + (unsigned)lane * 4u);
                     unsigned m = 0;
 #pragma unroll
                     for (int j4 = 0; j4 < CPT; j4 += 4) {
@@ -536,8 +547,8 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                     const bool two = hit != 0;
                     const int b1 = two ? __ffs(hit) - 1 : b0;
                     hit &= hit - 1;
-                    const float thr0 = gsc_lds_f(sb + Ly::THRW + (unsigned)b0 * 4u);
-                    const float thr1 = gsc_lds_f(sb + Ly::THRW + (unsigned)b1 * 4u);
+                    const float thr0 = gsc_lds_f(thrw + (unsigned)b0 * 4u);
+                    const float thr1 = gsc_lds_f(thrw + (unsigned)b1 * 4u);
                     float s0[CPT], s1[CPT];
                     {
                         const float4 v0 = gsc_lds_f4(sb + Ly::X + (unsigned)(pos + b0) * D * 4);
@@ -628,11 +639,14 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                 gsc_sts_f(etb + 4u * lane, sqrtf(__uint_as_float(gsc_kd(key)) / (float)D));  // enc:743 (term)
                                 already = gsc_lds_u8(sb + Ly::MFLAG + (unsigned)w);
                                 gsc_sts_u8(sb + Ly::MFLAG + (unsigned)w, already ? 2 : 1);   // 2: moved again in this round
-                                gsc_sts_i(sb + Ly::MOVED + 4u * (nm + lane - t0), w);
                                 gsc_atoms_or(sb + Ly::DIRTY + 4u * (unsigned)(w / CPT), 1u << (w % CPT));
                             }
                             const unsigned anyal = __ballot_sync(FULL, commit && already);
-                            nm += tstar - t0;
+                            {   // the moved list holds every centroid once
+                                const unsigned newm = __ballot_sync(FULL, commit && !already);
+                                if (commit && !already) gsc_sts_i(sb + Ly::MOVED + 4u * (unsigned)(nm + __popc(newm & ((1u << lane) - 1u))), w);
+                                nm += __popc(newm);
+                            }
                             __syncwarp();
                             // unresolved lanes take over the fresh keys of the committed rows
                             if (lane >= tstar && lane < nb) {
@@ -677,10 +691,13 @@ __global__ void __launch_bounds__(T) k_online(const GscFrame *__restrict__ frame
                                     const unsigned long long kk = gsc_lds_u64(sb + Ly::WKEY + (unsigned)(i * W + ww) * 8u);
                                     if (kk < k2) k2 = kk;
                                 }
-                                // k2 is the exact minimum over ALL unmoved centroids if one lies within the requested
-                                // distance dkreq; otherwise all that is known is "no unmoved centroid within dkreq"
+                                // k2 = minimum over the unmoved centroids whose lower bound is <= dkreq.  If its distance
+                                // is <= dkreq (or the scan was exhaustive) it is the exact minimum over ALL unmoved
+                                // centroids; otherwise all that is known is "no unmoved centroid within dkreq" (a survivor
+                                // beyond dkreq says nothing about the centroids that were filtered out), and the lane is
+                                // certified through Umine = dkreq like any other
                                 abest = k2; over = 0;
-                                exact = (k2 != GSC_KNONE) || !(dkreq < INFINITY);
+                                exact = !(dkreq < INFINITY) || (k2 != GSC_KNONE && __uint_as_float(gsc_kd(k2)) <= dkreq);
                                 if (!exact) Umine = dkreq;
                             }
                             c_exh += __popc(badmask);

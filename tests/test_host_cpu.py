@@ -9,8 +9,9 @@ import subprocess
 import numpy as np
 import pytest
 
+from tests.golden_util import EXCERPTS as GOLD
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
 
 
 @pytest.fixture(scope="session")

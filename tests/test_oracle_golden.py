@@ -1,17 +1,24 @@
 """CPU: the oracle against known answers worked out from the Pascal text and against the committed
 golden fixtures (tests/golden/*.npz, the reference's own test audio; make_golden.py made them)."""
-import glob
 import hashlib
 import os
 
 import numpy as np
 import pytest
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+from tests.golden_util import EXCERPTS as GOLD, FULL, check_stage, load_full, sha
 
 
 def test_fixtures_present():
-    assert len(GOLD) >= 5
+    assert len(GOLD) >= 5 and len(FULL) >= 16
+    # BASELINE.json configs[0..2] as written: every frame of my_test/test.wav, >= 8 lame_test tracks at K = 4096 /
+    # 12 bits, the opus_test stand-ins at K = 256 / 8 bits; wide epsilon bands and an overfull band are covered
+    names = [os.path.basename(p) for p in FULL]
+    assert sum(n.startswith("full_test_f") for n in names) == 3
+    assert sum(n.endswith("_k4096_12.npz") for n in names) >= 12 and sum(n.endswith("_k256_8.npz") for n in names) >= 4
+    sc = [load_full(p)[4] for p in FULL]
+    assert max(s["band_max"] for s in sc) > 64 and any(s["overfull"] > 0 for s in sc)
+    assert any(4 < s["band_max"] <= 64 and s["overfull"] == 0 for s in sc)
 
 
 # ---- known answers (hand-derived from enc:1638-1698, dec:6,88-96) ---------------------------
@@ -93,6 +100,33 @@ def test_oracle_reproduces_golden(oracle, path):
     dec, sr2 = O.decode(blob)
     assert sr2 == sr and hashlib.sha256(dec.tobytes()).digest() == g["decoded_sha256"].tobytes()
     assert O.snr_db(pcm, dec) == float(g["snr_db"])
+
+
+def _oracle_full(O, path):
+    pcm, sr, bits, K, scal, hs, hist = load_full(path)
+    div, v = O.find_attenuation_divider(pcm, 4, bits, return_v=True)
+    assert div == scal["divider"]
+    check_stage("divider_v", v, hs)
+    raw, attr, atten, feat, dst = O.make_chunks(pcm, 4, bits, div)
+    for n, a in (("attr", attr), ("atten", atten), ("feat", feat)):
+        check_stage(n, a, hs)
+    fr = O.encode_frame(pcm, chunk_bit_depth=bits, chunks_per_frame=K, band_all=1)
+    assert (fr.N, fr.R, fr.passes, fr.err, fr.overfull) == (scal["N"], scal["R"], scal["passes"], scal["err"], scal["overfull"])
+    for n, a in (("frame_dict", fr.dict), ("frame_datten", fr.datten), ("frame_index", fr.index), ("frame_attr", fr.attr)):
+        check_stage(n, a, hs)
+    blob = O.write_frame(fr, pcm.shape[0], 4, bits, sr)
+    assert hashlib.sha256(blob).hexdigest() == hs["gsc"] and len(blob) == scal["gsc_len"]
+    dec, _ = O.decode(blob)
+    assert sha(dec) == hs["decoded"] and O.snr_db(pcm, dec) == scal["snr_db"] and O.psy_a_delta(pcm, dec) == scal["psy_a_delta"]
+    return os.path.basename(path)
+
+
+def test_oracle_reproduces_full_frames(oracle):
+    """The oracle on every full-frame fixture (one host thread per frame: ~1 minute on 8 cores)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        done = list(ex.map(lambda p: _oracle_full(oracle, p), FULL))
+    assert len(done) == len(FULL)
 
 
 def test_round_trip_properties(oracle):
