@@ -258,19 +258,20 @@ int gsc_fetch_stream(gsc_ctx *ctx, int n_frames, int sample_rate, uint8_t *out, 
  * device (always true after gsc_encode_frames; after gsc_encode_frames_dev while the caller keeps its buffer). */
 int gsc_fetch_quality(gsc_ctx *ctx, int n_frames, uint64_t *sq_err, int64_t *samples);
 
-/* Debug hook for the parity tests: 1 = the online k-means kernel scores every
- * centroid in the exact operation order instead of using its lower-bound
- * filter.  Results are identical by construction; the tests check that. */
-void gsc_debug_set_online_exact(int on);
-/* Debug hook: 1 = the seeding kernel evaluates yakmo's sequential float prefix
- * sum with a one-warp serial chain instead of the exact parallel scan. */
-void gsc_debug_set_serial_scan(int on);
+/* Cross-check paths for the parity tests, per context (results are identical by construction; the tests check
+ * that).  flags = OR of: */
+#define GSC_DBG_ONLINE_EXACT  1u   /* online k-means scores every centroid exactly instead of using its filter */
+#define GSC_DBG_SEED_FULLSCAN 2u   /* seeding with the round-1 kernel: every step scans all points (block scan) */
+#define GSC_DBG_SEED_SERIAL   4u   /* ... and evaluates yakmo's float prefix sum with a one-warp serial chain */
+#define GSC_DBG_KNNFIT_DENSE  8u   /* KNNFit scans all entries twice instead of walking the norm window */
+#define GSC_DBG_LLOYD_OWNER   16u  /* Lloyd update by per-cluster owner threads (ordered sums) instead of the scatter */
+int gsc_ctx_set_debug(gsc_ctx *ctx, unsigned flags);
 /* Debug: counters of the last online k-means launch, 16 x uint64 per frame:
  * batches, points, re-filtered points, resolver rounds, full candidate lists,
  * candidates (lane 0); rest reserved (zero). */
 int gsc_debug_online_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
-/* Debug: cycles of the last seeding launch, 4 x uint64 per frame: seed pick,
- * distance pass, prefix scan, number of steps. */
+/* Debug: counters of the last seeding launch, 8 x uint64 per frame: cycles of seed pick, distance pass,
+ * summaries + chain, number of steps; windows evaluated exactly, blocks visited, windows re-summarised, chain cycles. */
 int gsc_debug_seed_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
 
 /* The library's natural logarithm (csrc/gsc_log.h: correctly rounded, plain IEEE double operations; the cepstral

@@ -27,7 +27,7 @@ EXPORTS = [
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
     "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_debug_set_online_exact", "gsc_debug_set_serial_scan", "gsc_debug_online_counters", "gsc_debug_seed_counters",
+    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_ctx_set_debug", "gsc_debug_online_counters", "gsc_debug_seed_counters",
 ]
 
 
@@ -199,8 +199,14 @@ class Context:
         self._ck(self.L.gsc_debug_online_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
 
+    DBG_ONLINE_EXACT, DBG_SEED_FULLSCAN, DBG_SEED_SERIAL, DBG_KNNFIT_DENSE, DBG_LLOYD_OWNER = 1, 2, 4, 8, 16
+
+    def set_debug(self, flags: int):
+        """Cross-check paths (include/gsc_cuda.h GSC_DBG_*); 0 = the product path."""
+        self._ck(self.L.gsc_ctx_set_debug(C.c_void_p(self.h), C.c_uint(flags)))
+
     def seed_counters(self, n_frames: int) -> np.ndarray:
-        out = np.zeros((n_frames, 4), np.uint64)
+        out = np.zeros((n_frames, 8), np.uint64)
         self._ck(self.L.gsc_debug_seed_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
 

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "gsc_kernels.cuh"
+#include "gsc_seed.cuh"
 #include "gsc_online.cuh"
 
 // ---------------------------------------------------------------------------
@@ -119,7 +120,9 @@ struct gsc_ctx {
     // device buffers
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
-        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke, sbytes, snb, sqerr;
+        use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke, sbytes, snb, sqerr,
+        perm, pns, xs, blo, bhi, wsum;
+    unsigned debug = 0;              // GSC_DBG_* (gsc_ctx_set_debug): cross-check paths for the parity tests
     HostBuf hpcm, hout, hstream;
     const short *pcm_view = nullptr;   // PCM of the last batch on the device (own buffer or the caller's)
     bool attr_set[4] = {false, false, false, false};
@@ -195,7 +198,8 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
-                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr, &c->scompact, &c->soffs};
+                      &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr, &c->scompact, &c->soffs,
+                      &c->perm, &c->pns, &c->xs, &c->blo, &c->bhi, &c->wsum};
     for (DevBuf *b : bufs) b->release();
     c->hsizes.release();
     c->hpcm.release();
@@ -374,22 +378,46 @@ static int stage_chunks(gsc_ctx *c, bool want_atten, bool want_dst, bool want_fe
         }                                     \
     } while (0)
 
-// Debug hook (tests): 1 = evaluate yakmo's float prefix sum with the one-warp serial chain
-// instead of the exact parallel scan; results must be identical.
-static int g_serial_scan = 0;
-extern "C" void gsc_debug_set_serial_scan(int on) { g_serial_scan = on ? 1 : 0; }
+extern "C" int gsc_ctx_set_debug(gsc_ctx *c, unsigned flags) {
+    if (!c) return set_err(GSC_ERR_ARG, "null context");
+    c->debug = flags;
+    if (c->peer) c->peer->debug = flags;
+    return GSC_OK;
+}
 
+// round-1 seeding kernel (every step scans all N points): kept as the cross-check of k_seed2
 template <int D>
-static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
+static int seed_launch_full(gsc_ctx *c, int init_type, bool want_seeds, int serial_scan) {
     size_t smem = (size_t)((c->maxN + 31) / 32) * 4;
     if (smem > 200 * 1024) return set_err(GSC_ERR_UNSUPPORTED, "frame too large for the seeding kernel");
-    TRY(c->sdbg.ensure(32 * (size_t)c->F));
-    CU(cudaMemsetAsync(c->sdbg.p, 0, 32 * (size_t)c->F, c->stream));
     SMEM_OPTIN(k_seed<D>, smem);
     LAUNCH(c, k_seed<D>, c->F, GSC_SEED_THREADS, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), init_type,
            c->pnorm.as<float>(), c->up.as<float>(), c->r.as<float>(), c->sid.as<int>(),
            want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax,
-           g_serial_scan, c->sdbg.as<unsigned long long>());
+           serial_scan, c->sdbg.as<unsigned long long>());
+    return GSC_OK;
+}
+
+// k_seed_prep + k_seed2 (gsc_seed.cuh): norm-bucketed distance pass, window summaries, exact chain
+template <int D>
+static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
+    TRY(c->sdbg.ensure(64 * (size_t)c->F));
+    CU(cudaMemsetAsync(c->sdbg.p, 0, 64 * (size_t)c->F, c->stream));
+    if (c->debug & (GSC_DBG_SEED_FULLSCAN | GSC_DBG_SEED_SERIAL))
+        return seed_launch_full<D>(c, init_type, want_seeds, (c->debug & GSC_DBG_SEED_SERIAL) ? 1 : 0);
+    const size_t smem = gsc_seed2_smem(c->maxN);
+    if (smem > 220 * 1024) return set_err(GSC_ERR_UNSUPPORTED, "frame too large for the seeding kernel (%d chunks)", c->maxN);
+    const size_t n = (size_t)c->sumN, nwin = n / GSC_SW + (size_t)c->F + 2;
+    TRY(c->perm.ensure(4 * n)); TRY(c->pns.ensure(4 * n)); TRY(c->xs.ensure(4 * n * D));
+    TRY(c->blo.ensure(4 * nwin)); TRY(c->bhi.ensure(4 * nwin)); TRY(c->wsum.ensure(16 * nwin));
+    LAUNCH(c, k_seed_prep<D>, c->F, 512, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->pnorm.as<float>(),
+           c->perm.as<int>(), c->pns.as<float>(), c->xs.as<float>(), c->blo.as<float>(), c->bhi.as<float>());
+    SMEM_OPTIN(k_seed2<D>, smem);
+    LAUNCH(c, k_seed2<D>, c->F, GSC_SEED2_T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->xs.as<float>(),
+           c->pns.as<float>(), c->perm.as<int>(), c->blo.as<float>(), c->bhi.as<float>(), init_type,
+           c->r.as<float>(), c->up.as<float>(), c->sid.as<int>(), c->wsum.as<int4>(),
+           want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax,
+           c->sdbg.as<unsigned long long>());
     return GSC_OK;
 }
 
@@ -421,9 +449,7 @@ static int stage_assign(gsc_ctx *c, int D, bool want_dist) {
 
 // Lloyd update into `acc` (Double [F][Kmax][D+1]; default: the context's own buffer), then means.
 static int stage_lloyd_sums(gsc_ctx *c, int D, double *acc) {
-    static int owner = -1;   // GSC_LLOYD_OWNER=1: per-cluster owner threads (ordered sums) instead of the scatter
-    if (owner < 0) { const char *e = getenv("GSC_LLOYD_OWNER"); owner = (e && e[0] == '1') ? 1 : 0; }
-    if (owner) {
+    if (c->debug & GSC_DBG_LLOYD_OWNER) {   // per-cluster owner threads (ordered sums) instead of the scatter
         dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
         DISPATCH_D(D, LAUNCH(c, k_owner_sums_d<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
                              c->labels.as<int>(), acc, c->Kmax));
@@ -449,12 +475,11 @@ static int stage_lloyd_update(gsc_ctx *c, int D) {
 // Slack on the candidate threshold of the online kernel (a tuning knob: any value gives the same
 // results, see gsc_online.cuh phase 2).  GSC_ONLINE_SLACK overrides the default.
 static float online_slack() {
-    static float v = -1.0f;
-    if (v < 0.0f) {
+    static const float v = [] {
         const char *e = getenv("GSC_ONLINE_SLACK");
-        float x = e ? (float)atof(e) : 1.0f;
-        v = (x >= 1.0f && x <= 16.0f) ? x : 1.0f;
-    }
+        const float x = e ? (float)atof(e) : 1.0f;
+        return (x >= 1.0f && x <= 16.0f) ? x : 1.0f;
+    }();
     return v;
 }
 
@@ -475,17 +500,13 @@ static double int_power10_neg(int prec) {  // IntPower(10.0, -Precision), enc:76
     return 1.0 / p;
 }
 
-static int g_force_exact = -1;
-// Debug hook (tests): 1 = score every centroid exactly in the online kernel
-// instead of using the lower-bound filter; results must be identical.
-extern "C" void gsc_debug_set_online_exact(int on) { g_force_exact = on ? 1 : 0; }
 // Debug: counters of the last online k-means launch, 8 x uint64 per frame:
 // batches, points, exhaustive points, cuts (verification), cuts (list overflow), candidates.
 // Debug: cycles of the last seeding launch, 4 x uint64 per frame: pick, distance pass, prefix scan, steps.
 extern "C" int gsc_debug_seed_counters(gsc_ctx *c, unsigned long long *out, int n_frames) {
     if (!c || !out || n_frames > c->F || !c->sdbg.p) return set_err(GSC_ERR_ARG, "bad arguments");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(out, c->sdbg.p, 32 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out, c->sdbg.p, 64 * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return GSC_OK;
 }
@@ -496,14 +517,6 @@ extern "C" int gsc_debug_online_counters(gsc_ctx *c, unsigned long long *out, in
     CU(cudaStreamSynchronize(c->stream));
     return GSC_OK;
 }
-static int force_exact_flag() {
-    if (g_force_exact < 0) {
-        const char *e = getenv("GSC_ONLINE_EXACT");
-        g_force_exact = (e && e[0] == '1') ? 1 : 0;
-    }
-    return g_force_exact;
-}
-
 // online k-means; labels buffer must already hold per-point guesses
 static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     TRY(c->passes.ensure(4 * (size_t)c->F)); TRY(c->err.ensure(8 * (size_t)c->F));
@@ -512,7 +525,7 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     CU(cudaMemsetAsync(c->err.p, 0, 8 * (size_t)c->F, c->stream));
     CU(cudaMemsetAsync(c->dbg.p, 0, 128 * (size_t)c->F, c->stream));
     const double tol = int_power10_neg(precision);
-    const int K = c->Kmax, fe = force_exact_flag();
+    const int K = c->Kmax, fe = (c->debug & GSC_DBG_ONLINE_EXACT) ? 1 : 0;
     // CTA shape by dictionary size: small K -> small CTAs so that several frames share an SM.  Only shapes that
     // compile without register spills are used (build.py checks).
     if (D == 8) {
@@ -561,9 +574,7 @@ static int stage_knnfit(gsc_ctx *c, bool want_band) {
     CU(cudaMemsetAsync(c->use.p, 0, 4 * fk, c->stream));
     CU(cudaMemsetAsync(c->overfull.p, 0, 4 * (size_t)c->F, c->stream));
     dim3 grid((c->maxN + 255) / 256, c->F);
-    static int dense = -1;   // GSC_KNNFIT_DENSE=1: the plain two-pass scan over all entries (A/B and cross-check)
-    if (dense < 0) { const char *e = getenv("GSC_KNNFIT_DENSE"); dense = (e && e[0] == '1') ? 1 : 0; }
-    if (!dense) {
+    if (!(c->debug & GSC_DBG_KNNFIT_DENSE)) {   // (dense: the plain two-pass scan over all entries, cross-check)
         TRY(c->kv.ensure(4 * fk * cs)); TRY(c->kn.ensure(4 * fk)); TRY(c->ke.ensure(4 * fk));
         int r2 = 1;
         while (r2 < c->Kmax) r2 <<= 1;
@@ -1160,8 +1171,7 @@ extern "C" int gsc_fetch_quality(gsc_ctx *c, int n_frames, uint64_t *sq_err, int
 
 // ---- two lanes per context ---------------------------------------------------------------------
 static int lanes_enabled() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("GSC_STREAMS"); v = (e && atoi(e) == 1) ? 0 : 1; }
+    static const int v = [] { const char *e = getenv("GSC_STREAMS"); return (e && atoi(e) == 1) ? 0 : 1; }();
     return v;
 }
 #define GSC_SPLIT_MIN 16   // batches below this run on one stream
@@ -1175,6 +1185,7 @@ static int plan_lanes(gsc_ctx *c, int n_frames) {
         c->peer = gsc_create(c->device);
         if (!c->peer) return GSC_ERR_CUDA;
     }
+    c->peer->debug = c->debug;
     for (int i = 0; i < n_frames; ++i) ((i & 1) ? c->idx_b : c->idx_a).push_back(i);
     return GSC_OK;
 }

@@ -232,6 +232,15 @@ struct GscOnLayout {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget of one SM");
 };
 
+// GSC_ONLINE_CHECKS (debug builds of tools/spill_probe.py only; compute-sanitizer is not available on the GPU pool):
+// bounds of every shared-memory index the kernel forms, and the invariants of its cross-warp hand-offs (register
+// filter copy == shared rows unless flagged dirty, empty candidate lists / clear moved flags at a batch start).
+// Failures are counted in the launch's debug buffer (slot 8: count, slot 9: first failing source line).
+#ifdef GSC_ONLINE_CHECKS
+#define GSC_CHK(cond) do { if (!(cond) && chk) { atomicAdd(chk, 1ull); atomicCAS(chk + 1, 0ull, (unsigned long long)__LINE__); } } while (0)
+#else
+#define GSC_CHK(cond) ((void)0)
+#endif
 // GSC_ONLINE_MAXNREG (debug builds of tools/spill_probe.py only): cap the registers below what the kernel needs, so
 // that ptxas spills -- the results must not change.
 #ifdef GSC_ONLINE_MAXNREG
@@ -259,7 +268,10 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
     const unsigned sb = gsc_opaque(gsc_smem_u32(smraw));
 
     // low word of a key for the centroid in `slot`
-    auto idword = [&](int slot) -> unsigned { return ((unsigned)gsc_lds_u16(sb + Ly::S2O + 2u * (unsigned)slot) << 16) | (unsigned)slot; };
+#ifdef GSC_ONLINE_CHECKS
+    unsigned long long *chk = dbg ? dbg + (long long)frames[blockIdx.x].slot * 16 + 8 : nullptr;
+#endif
+    auto idword = [&](int slot) -> unsigned { GSC_CHK(slot >= 0 && slot < T * CPT); return ((unsigned)gsc_lds_u16(sb + Ly::S2O + 2u * (unsigned)slot) << 16) | (unsigned)slot; };
     const GscFrame f = frames[blockIdx.x];
     const int K = f.K, N = f.N;
     if (K <= 0) return;
@@ -388,6 +400,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
             for (int t = tid; t < tn * D; t += T) gsc_sts_f(sb + Ly::X + 4u * t, Xf[(long long)base * D + t]);
             for (int t = tid; t < tn; t += T) {
                 int gg = lab[base + t];
+                GSC_CHK(gg >= 0 && gg < KP);
                 gsc_sts_i(sb + Ly::G + 4u * t, (gg < 0 || gg >= KP) ? 0 : gg);   // slot of the previous pass's centroid
             }
             __syncthreads();  // (B)
@@ -426,6 +439,22 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                         }
                     }
                 }
+#ifdef GSC_ONLINE_CHECKS
+                {   // hand-off invariants at a batch start
+#pragma unroll
+                    for (int p2 = 0; p2 < CPT / 2; ++p2) {
+                        const float4 ra = gsc_lds_f4(sb + Ly::C + (unsigned)(first + 2 * p2) * D * 4);
+                        const float4 rb = gsc_lds_f4(sb + Ly::C + (unsigned)(first + 2 * p2 + 1) * D * 4);
+                        const unsigned long long want[4] = {gsc_pk2(ra.x, rb.x), gsc_pk2(ra.y, rb.y), gsc_pk2(ra.z, rb.z), gsc_pk2(ra.w, rb.w)};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) GSC_CHK(fcp[p2][k] == want[k]);
+                        GSC_CHK(hp[p2] == gsc_lds_u64(sb + Ly::H + (unsigned)(first + 2 * p2) * 4u));
+                    }
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) GSC_CHK(gsc_lds_u8(sb + Ly::MFLAG + (unsigned)(first + j)) == 0);
+                    GSC_CHK(gsc_lds_i(sb + Ly::DIRTY + 4u * cell) == 0);
+                }
+#endif
                 // ============ phase 1: all warps, codebook frozen ============
                 float xb[D];              // lane b of every warp: point pos+b
                 float Umine = INFINITY;   // ... and its bound
@@ -465,6 +494,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                 constexpr int QCAP = (GSC_ON_B * GSC_ON_B * 8) / (4 * W);   // the FK region is free in phase 1
                 const unsigned q_a = sb + Ly::FK + (unsigned)warp * (unsigned)(QCAP * 4);
                 auto score_append = [&](int slot, int b) {
+                    GSC_CHK(slot >= 0 && slot < KP && b >= 0 && b < nb);
                     float x[D], rw[D];
                     gsc_lds_row<D>(sb + Ly::X + (unsigned)(pos + b) * D * 4, x);
                     gsc_lds_row<D>(sb + Ly::C + (unsigned)slot * D * 4, rw);
@@ -627,6 +657,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                             const bool commit = lane >= t0 && lane < tstar;
                             int already = 0;
                             if (commit) {
+                                GSC_CHK(w >= 0 && w < KP && gsc_lds_u16(sb + Ly::S2O + 2u * (unsigned)w) < K && base + pos + lane < N);
                                 gsc_sts_row<D>(sb + Ly::C + (unsigned)w * D * 4, rn);
                                 {
                                     float nc = 0.0f;
@@ -646,6 +677,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                                 const unsigned newm = __ballot_sync(FULL, commit && !already);
                                 if (commit && !already) gsc_sts_i(sb + Ly::MOVED + 4u * (unsigned)(nm + __popc(newm & ((1u << lane) - 1u))), w);
                                 nm += __popc(newm);
+                                GSC_CHK(nm <= B);
                             }
                             __syncwarp();
                             // unresolved lanes take over the fresh keys of the committed rows
@@ -704,7 +736,10 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                         }
                         // ---- R1: proposals of the unresolved lanes ----
                         if (t0 >= nb) {
-                            // hand over to the next batch
+                            // hand over to the next batch (the flags other lanes wrote above are cleared here: make the
+                            // order of those stores explicit)
+                            __syncwarp();
+                            GSC_CHK(gsc_lds_i(sb + Ly::LISTN + 4u * lane) >= 0);
                             if (lane < nm) gsc_sts_u8(sb + Ly::MFLAG + (unsigned)gsc_lds_i(sb + Ly::MOVED + 4u * lane), 0);
                             gsc_sts_i(sb + Ly::LISTN + 4u * lane, 0);
                             if (lane == 0) gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
@@ -777,6 +812,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                         const int ne = gsc_lds_i(sb + Ly::NE);
                         for (int i = 0; i < ne; ++i) {
                             const int pe = gsc_lds_i(sb + Ly::EPTS + 4u * i);
+                            GSC_CHK(ne <= B && pe >= pos && pe < pos + nb);
                             const float thr = gsc_lds_f(sb + Ly::ETHRS + 4u * i);
                             float x[D];
                             gsc_lds_row<D>(sb + Ly::X + (unsigned)pe * D * 4, x);

@@ -110,7 +110,10 @@ def run_full(pcm, sr, bits, K):
                 N=int(len(feat)), band_max=int(band.max()), band_gt4=int((band > 4).sum()),
                 band_rule_differs=int((fit["best"] != fit["best_all"]).sum()),
                 dbl_diff=int(fit["dbl_diff"].sum()), snr_db=float(O.snr_db(pcm, dec)),
-                psy_a_delta=float(O.psy_a_delta(pcm, dec)), gsc_len=len(blob))
+                psy_a_delta=float(O.psy_a_delta(pcm, dec)),
+                # encoder-side reconstruction (enc:487-522), what the encoder prints as PsyADelta (enc:2026)
+                psy_a_delta_enc=float(O.psy_a_delta(pcm, O.reconstruct_frame(fr, pcm.shape[0], pcm.shape[1], cs, bits))),
+                gsc_len=len(blob))
     hs = dict(divider_v=sha(v), attr=sha(attr), atten=sha(atten), feat=sha(feat), seeds=sha(seeds), cen0=sha(canon(cen0)),
               labels=sha(labels), cen=sha(canon(cen)), dict_means=sha(d["means"]), dict_q=sha(d["dict"]),
               dict_atten=sha(d["datten"]), dict_counts=sha(d["counts"]), best_all=sha(fit["best_all"]),

@@ -78,23 +78,51 @@ def test_yakmo_seeding(ctx, oracle, K, seconds):
 
 
 def test_yakmo_seeding_full_size_and_scan_modes(ctx, oracle):
-    """Full-size frame (N ~ 96k, K = 4096): the exact parallel evaluation of yakmo's sequential float
-    prefix sum must give the oracle's seed sequence, and so must the one-warp serial chain."""
-    import soundchunks_b200.binding as b
+    """Full-size frame (N ~ 96k, K = 4096): the incremental seeding kernel (window summaries + exact chain,
+    gsc_seed.cuh) must give the oracle's seed sequence, and so must the two cross-check evaluations (every step a
+    block-wide exact scan of all points; a one-warp serial chain)."""
     pcm = _quiet(_audio(4.0, 48000, 2, 77))
     raw, attr, atten, feat, dst = oracle.make_chunks(pcm, 4, 12, 6)
     c_ref, l_ref, s_ref = oracle.yakmo(feat, 4096)
     c_gpu, l_gpu, s_gpu = ctx.yakmo(feat, 4096)
     assert np.array_equal(s_gpu, s_ref), f"first divergence at seed {int(np.argmax(s_gpu != s_ref))}"
-    assert _same_f32(c_gpu, c_ref)
-    lib = b.load_library()
-    lib.gsc_debug_set_serial_scan(1)
-    try:
-        c2, l2, s2 = ctx.yakmo(feat[:20000], 300)
-    finally:
-        lib.gsc_debug_set_serial_scan(0)
+    assert _same_f32(c_gpu, c_ref) and np.array_equal(l_gpu, l_ref)
     c3, l3, s3 = ctx.yakmo(feat[:20000], 300)
-    assert np.array_equal(s2, s3) and _same_f32(c2, c3) and np.array_equal(l2, l3)
+    for flag in (ctx.DBG_SEED_FULLSCAN, ctx.DBG_SEED_SERIAL):
+        ctx.set_debug(flag)
+        try:
+            c2, l2, s2 = ctx.yakmo(feat[:20000], 300)
+        finally:
+            ctx.set_debug(0)
+        assert np.array_equal(s2, s3) and _same_f32(c2, c3) and np.array_equal(l2, l3)
+    ctx.set_debug(ctx.DBG_SEED_FULLSCAN)
+    try:
+        c4, l4, s4 = ctx.yakmo(feat, 4096)
+    finally:
+        ctx.set_debug(0)
+    assert np.array_equal(s4, s_ref) and _same_f32(c4, c_ref)
+
+
+@pytest.mark.parametrize("kind", ["ragged", "silence_runs", "duplicates", "tiny"])
+def test_yakmo_seeding_edge_cases(ctx, oracle, kind):
+    """Inputs that stress the prefix-sum machinery: window-ragged N, long runs of zero distances (digital silence:
+    duplicate points), massively duplicated chunks, and N barely above K."""
+    rng = np.random.default_rng(17)
+    pcm = _quiet(_audio(0.45, 44100, 1, 31))
+    if kind == "silence_runs":
+        pcm = pcm.copy(); pcm[:, 3000:9000] = 0; pcm[:, 12000:12800] = 0
+    if kind == "duplicates":
+        pcm = np.ascontiguousarray(np.tile(pcm[:, :2000], (1, 9)))
+    raw, attr, atten, feat, dst = oracle.make_chunks(pcm, 4, 12, 6)
+    if kind == "ragged":
+        feat = np.ascontiguousarray(feat[:4099])
+    K = {"ragged": 300, "silence_runs": 256, "duplicates": 200, "tiny": 64}[kind]
+    if kind == "tiny":
+        feat = np.ascontiguousarray(feat[:65])
+    c_ref, l_ref, s_ref = oracle.yakmo(feat, K)
+    c_gpu, l_gpu, s_gpu = ctx.yakmo(feat, K)
+    assert np.array_equal(s_gpu, s_ref), f"{kind}: first divergence at seed {int(np.argmax(s_gpu != s_ref))}"
+    assert _same_f32(c_gpu, c_ref) and np.array_equal(l_gpu, l_ref)
 
 
 def test_yakmo_random_init_and_iters(ctx, oracle):
@@ -120,16 +148,14 @@ def test_online_kmeans_bit_exact(ctx, oracle, K, seconds, passes):
 
 def test_online_kmeans_filter_equals_exhaustive(ctx, oracle):
     """The lower-bound filter must give exactly what scoring every centroid exactly gives."""
-    import soundchunks_b200.binding as b
     pcm, raw, attr, feat = _features(oracle, 0.3)
     c0, _, _ = oracle.yakmo(feat, 512)
     fast = ctx.knn_scan_reduce(feat, c0, 3, 10)
-    lib = b.load_library()
-    lib.gsc_debug_set_online_exact(1)
+    ctx.set_debug(ctx.DBG_ONLINE_EXACT)
     try:
         slow = ctx.knn_scan_reduce(feat, c0, 3, 10)
     finally:
-        lib.gsc_debug_set_online_exact(0)
+        ctx.set_debug(0)
     assert fast[2] == slow[2] and fast[3] == slow[3]
     assert np.array_equal(fast[1], slow[1])
     assert np.array_equal(fast[0].view(np.uint32), slow[0].view(np.uint32))

@@ -26,7 +26,9 @@ for K, bits in cfgs:
     print({k: round(v, 2) for k, v in st["stage_ms"].items()})
     sd = ctx.seed_counters(min(nf, 2)).astype(float)
     for r in sd:
-        print(f"   seeding cycles/step: pick {r[0] / max(r[3], 1):.0f} distance {r[1] / max(r[3], 1):.0f} scan {r[2] / max(r[3], 1):.0f}")
+        st_ = max(r[3], 1)
+        print(f"   seeding cycles/step: pick {r[0] / st_:.0f} distance {r[1] / st_:.0f} summaries+chain {r[2] / st_:.0f} (chain {r[7] / st_:.0f}); "
+              f"per step: exact windows {r[4] / st_:.1f} blocks visited {r[5] / st_:.1f} windows re-summarised {r[6] / st_:.1f}")
     cn = ctx.online_counters(min(nf, 8)).astype(float)
     for r in cn[:4]:
         b, p, e, rd, ov, ca = r[:6]

@@ -35,6 +35,8 @@ def main():
         for cap in CAPS:
             sp = b.build_variant(os.path.join(VDIR, f"libgsc_cuda_r{cap}.so"), cap)
             print("cap", cap, "spilling k_online shapes:", len(sp))
+        sp = b.build_variant(os.path.join(VDIR, "libgsc_cuda_checks.so"), 0, checks=True)
+        print("checks build, spilling k_online shapes:", len(sp))
         return
     if cmd == "oracle":
         from concurrent.futures import ThreadPoolExecutor
@@ -69,11 +71,20 @@ def main():
                     if not ok:
                         d = np.nonzero(lab != g[f"lab{P}"])[0]
                         msg += f" first label diff at {d[0] if len(d) else -1} ({len(d)} differ), oracle it={int(g[f'it{P}'])} err={float(g[f'err{P}'])!r}"
+                    cn = ctx.online_counters(1)[0]
+                    if cn[8]:
+                        msg += f" CHECKS FAILED: {int(cn[8])} (first at gsc_online.cuh:{int(cn[9])})"
+                    elif tag == "checks":
+                        msg += " checks clean"
                     print(msg, flush=True)
         return
     # run: shipped build + every variant, each in its own process (the library path is fixed at import)
-    libs = [("shipped", None)] + [(f"r{c}", os.path.join(VDIR, f"libgsc_cuda_r{c}.so")) for c in CAPS]
+    libs = [("shipped", None)] + [(f[len("libgsc_cuda_"):-3], os.path.join(VDIR, f)) for f in sorted(os.listdir(VDIR))
+                                   if f.startswith("libgsc_cuda_") and f.endswith(".so")]
+    only = sys.argv[2:]                      # optional: tags to run (e.g. `run checks`)
     for tag, so in libs:
+        if only and tag not in only:
+            continue
         env = dict(os.environ)
         if so:
             if not os.path.exists(so):
