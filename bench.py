@@ -16,8 +16,11 @@ through the public host-buffer call gsc_encode_frames (pinned staging + H2D + al
 dictionary/indexes inside the timed region).
 
 --impl reference times the CPU restatement of the reference (oracle/, all host threads) on a
-bounded sample of the same workload; the FreePascal encoder itself cannot be built here
-(DESIGN.md).  That and the cpu_baseline leg are the only places this file touches oracle/.
+bounded sample of the SAME workload: one 4 s frame of the same generator per host core and step,
+searched the way the binary searches (ANN-1.1.2-style kd-tree rebuilt every pass); the FreePascal
+encoder itself cannot be built here.  That, the cpu_baseline leg and the parity
+probe (two of the step's frames against oracle.encode_frame, outside the timed region) are the
+only places this file touches oracle/.
 """
 from __future__ import annotations
 
@@ -58,22 +61,26 @@ def parse_args():
     ap.add_argument("--mode", default="online", choices=["online", "lloyd"],
                     help="online = the reference's rule (bit-exact vs the oracle); lloyd = batch Lloyd substitution")
     ap.add_argument("--lloyd-iters", type=int, default=30)
-    ap.add_argument("--cpu-sample-seconds", type=float, default=1.0,
-                    help="length of each frame of the CPU baseline sample")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=FRAME_SECONDS,
+                    help="length of each frame of the CPU sample (default: the workload's own 4 s frames)")
+    ap.add_argument("--cpu-search", default="kdtree", choices=["kdtree", "exact"],
+                    help="CPU arm: ANN-style kd-tree rebuilt per pass (what the binary does) or exhaustive exact search")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lloyd", action="store_true", help="skip the secondary Lloyd-mode leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the k256 / strong_1h / split_frame legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity probe against the oracle")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------
 # synthetic workload
 # ---------------------------------------------------------------------------------------------
-def make_frames(n, seconds, seed):
+def make_frames(n, seconds, seed, sample_rate=SAMPLE_RATE):
     """n distinct synthetic frames, planar int16 [C][S]; 16 distinct signals are generated and
     re-mixed (channel swap / time reversal / polarity) so that the generation stays short."""
     from soundchunks_b200.synth import synth_frames
-    base = synth_frames(min(n, 16), seconds, SAMPLE_RATE, CHANNELS, seed=seed, chunk_size=CHUNK_SIZE)
+    base = synth_frames(min(n, 16), seconds, sample_rate, CHANNELS, seed=seed, chunk_size=CHUNK_SIZE)
     out = []
     for i in range(n):
         f = base[i % len(base)]
@@ -144,15 +151,26 @@ class ClockSampler:
 # CPU arm: the oracle (C restatement of the reference path), frame-parallel over host threads
 # like ProcThreadPool (mtprocs.pas:598-602, enc:1449)
 # ---------------------------------------------------------------------------------------------
-def cpu_encode_sample(frames, K, bits, threads):
+def cpu_encode_sample(frames, K, bits, threads, search="kdtree"):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import gsc_oracle as O
     O.build()
-    p = O.default_params(chunk_bit_depth=bits, chunks_per_frame=K)
+    # kmeans_mode 3: enc:699-765 / 915-965 through an ANN-1.1.2-style kd-tree rebuilt every pass, as the binary does
+    # (leaf distances on the live rows, planes from the pass start); 0: exhaustive exact search (the GPU's contract)
+    p = O.default_params(chunk_bit_depth=bits, chunks_per_frame=K, kmeans_mode=3 if search == "kdtree" else 0)
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         res = list(ex.map(lambda f: O.encode_frame(f, p), frames))
     return time.perf_counter() - t0, res
+
+
+def cpu_sample_text(cores, seconds, res, K, search, extra=""):
+    how = ("nearest centroid / 64 nearest variants through an ANN-1.1.2-style kd-tree rebuilt every pass (enc:729, 945), "
+           "as the binary searches" if search == "kdtree" else "exhaustive exact search (vectorised)")
+    return (f"{cores} frames x {seconds:g} s of the same synthetic {SAMPLE_RATE} Hz stereo generator per step "
+            f"(N={res[0].N} chunks/frame, K={K}), one frame per host thread{extra}; online passes "
+            f"{[r.passes for r in res]}; C restatement of encoder.lpr's DoFrame (the FreePascal binary cannot be built "
+            f"here); {how}")
 
 
 def run_reference(args, rank):
@@ -162,23 +180,21 @@ def run_reference(args, rank):
     frames = make_frames(cores, args.cpu_sample_seconds, seed=4321)
     audio_s = sum(f.shape[1] for f in frames) / SAMPLE_RATE
     for _ in range(min(args.warmup, 1)):        # one warm-up pass is enough for a CPU loop
-        cpu_encode_sample(frames, args.chunks_per_frame, args.bits, cores)
+        cpu_encode_sample(frames, args.chunks_per_frame, args.bits, cores, args.cpu_search)
     t = 0.0
-    passes = []
     for _ in range(args.steps):
-        dt, res = cpu_encode_sample(frames, args.chunks_per_frame, args.bits, cores)
+        dt, res = cpu_encode_sample(frames, args.chunks_per_frame, args.bits, cores, args.cpu_search)
         t += dt
-        passes = [r.passes for r in res]
     value = audio_s * args.steps / t
-    sample = (f"{cores} frames x {args.cpu_sample_seconds:g} s of the same synthetic {SAMPLE_RATE} Hz stereo audio "
-              f"per step (N={res[0].N} chunks/frame, K={args.chunks_per_frame}), one frame per host thread; "
-              f"online passes {passes}; the port searches every centroid (vectorised) where the reference walks an "
-              f"ANN kd-tree, same results")
+    sample = cpu_sample_text(cores, args.cpu_sample_seconds, res, args.chunks_per_frame, args.cpu_search)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.frames, FRAME_SECONDS),
+        # what one step of THIS arm really ran (a bounded sample of the workload `config` names)
+        "sample": {"frames_per_step": cores, "frame_seconds": args.cpu_sample_seconds, "chunks_per_frame_N": res[0].N,
+                   "search": args.cpu_search, "same_frame_shape_as_config": args.cpu_sample_seconds == FRAME_SECONDS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -282,6 +298,7 @@ def main():
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = ctx.stats()["kernel_launches"] + args.steps  # + the L2 flush fill kernel of each step
     res = ctx.fetch_results(layout, params)                 # also collects the stage events of the last step
+    dev_stream, dev_sizes = ctx.fetch_stream(F, SAMPLE_RATE)   # .gsc bytes of the device-resident leg's last step
     stage_acc = ctx.stats()["stage_ms"]                     # last step's stage times (CUDA events, ctx stream)
     passes = [r.passes for r in res]
     Ns = [r.N for r in res]
@@ -298,13 +315,20 @@ def main():
         flops = sum(2.0 * n * K * D * (args.lloyd_iters + 1) for n in Ns)
         kname = "k_assign"
     # the library runs a batch on two streams (even / odd frames); stage_ms are the CUDA-event stage times of both
-    # lanes ADDED UP.  The lanes overlap, so the k-means kernels are busy for at most km_ms / 2 of wall time when both
-    # lanes run side by side: the roofline uses km_ms / 2 ... km_ms; the conservative (full sum) figure is reported.
+    # lanes ADDED UP; the roofline divides by the UNION of the two lanes' k-means intervals (wall time with a
+    # k-means kernel running on either stream)
     km_ms = ctx.stage_busy_ms("kmeans")     # wall time with a k-means kernel running on either stream (union)
     achieved = flops / (km_ms * 1e-3) / 1e12 if km_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:    # dram bytes per launch of the dominant kernel, from the committed `ncu --set full` capture at the bench shape
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
+            tj = json.load(fh)
+        traffic, traffic_src = tj.get(kname, {}).get("dram_bytes_per_launch"), tj.get(kname, {}).get("source")
+    except (OSError, ValueError):
+        pass
     roofline = {
         "bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+        "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic, "traffic_source": traffic_src,
         "note": "algorithmic flops = 2*N*K*D per pass (dense count, SURVEY.md 8d), D=8; duration = CUDA events "
                 "around the k-means stage of the last timed step; peak = FFMA probe measured in this run "
                 "(MEASURED_PEAKS.json has no FP32 figure); share of step = %.3f" % (km_ms / max(stage_acc["total"], 1e-9)),
@@ -316,7 +340,7 @@ def main():
         # host PCM in -> .gsc bytes out: gsc_encode_frames (pinned staging, H2D, all kernels, the device-side
         # .gsc packer) + gsc_fetch_stream (D2H of the stream) -- what an encoder front-end calls per batch
         import hashlib
-        ref_stream, _ = ctx.fetch_stream(F, SAMPLE_RATE)        # stream of the device-resident leg's last step
+        ref_stream = dev_stream
         ctx.encode_to_stream(frames, SAMPLE_RATE, params)       # warm-up (allocates the pinned staging)
         barrier()
         ctx.reset_stats()
@@ -361,16 +385,87 @@ def main():
                               "note": "dense count 2*N*K*D*(iters+1) / wall time with the stage running on either stream; "
                                       "other stages of the other stream share the GPU during that time"}}
 
+    # parity probe, OUTSIDE every timed region: two frames of the step's batch (one per internal lane) re-encoded by the
+    # CPU oracle (exhaustive exact search: the library's contract) and compared bit for bit, fields and .gsc bytes
+    parity = None
+    if rank == 0 and not args.no_parity and args.mode == "online":
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import gsc_oracle as O
+        probe = [0, 1] if F > 1 else [0]
+        op = O.default_params(chunk_bit_depth=args.bits, chunks_per_frame=K, band_all=1)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(len(probe)) as ex:
+            refs = list(ex.map(lambda i: O.encode_frame(frames[i], op), probe))
+        gblob, gsz = dev_stream, dev_sizes
+        goff = np.concatenate([[0], np.cumsum(gsz)])
+        same = []
+        for i, ref in zip(probe, refs):
+            r = res[i]
+            ok = ((r.N, r.R, r.divider, r.passes, r.err, r.overfull) == (ref.N, ref.R, ref.divider, ref.passes, ref.err, ref.overfull)
+                  and np.array_equal(r.dict, ref.dict) and np.array_equal(r.datten, ref.datten)
+                  and np.array_equal(r.index, ref.index) and np.array_equal(r.attr, ref.attr)
+                  and gblob[goff[i]:goff[i + 1]] == O.write_frame(ref, CHANNELS, CHUNK_SIZE, args.bits, SAMPLE_RATE))
+            same.append(bool(ok))
+        parity = {"frames": probe, "identical": all(same), "per_frame": same, "passes": [r.passes for r in refs],
+                  "oracle_s": round(time.perf_counter() - t0, 1),
+                  "what": "frames of the timed batch vs oracle.encode_frame (N=%d, K=%d, <=100 passes): divider, passes, Double "
+                          "error sum, dictionary, attenuations, indexes, attributes and .gsc bytes" % (refs[0].N, K)}
+        assert parity["identical"], "GPU result differs from the oracle: %r" % (parity,)
+
+    # extra legs (driver-visible): BASELINE.json configs[2] (K=256 / 8-bit) and configs[4] (1 h of 48 kHz stereo = 900 frames,
+    # STRONG scaling: the one stream's frames are split over the ranks)
+    extras = {}
+    if not args.no_extras and args.mode == "online":
+        def timed_dev(devbuf, lay, prm, nsteps=1):
+            ctx.encode_frames_dev(devbuf.data_ptr(), lay, prm)     # warm-up (buffers of this shape)
+            ctx.synchronize()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(nsteps):
+                with torch.cuda.stream(stream):
+                    flush.zero_()
+                ctx.encode_frames_dev(devbuf.data_ptr(), lay, prm)
+            a1.record(stream)
+            ctx.synchronize()
+            barrier()
+            return max_over_ranks(a0.elapsed_time(a1)) / nsteps
+        # -- k256
+        p256 = sc.default_params(chunk_bit_depth=8, chunks_per_frame=256)
+        ms = timed_dev(dev, layout, p256)
+        r256 = ctx.fetch_results(layout, p256)
+        km = ctx.stage_busy_ms("kmeans")
+        fl = sum(2.0 * r.N * 256 * D * r.passes for r in r256)
+        extras["k256"] = {"config": "BASELINE.json configs[2] shape: ChunkCount=256, 8-bit chunks, same %d frames per GPU" % F,
+                          "value": total_audio / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "online_passes_median": statistics.median([r.passes for r in r256]),
+                          "k_online_dense_tflops": fl / (km * 1e-3) / 1e12 if km > 0 else None,
+                          "k_online_frac_of_fp32_peak": fl / (km * 1e-3) / 1e12 / fp32_peak if km > 0 and fp32_peak else None,
+                          "stages_ms": {k: round(v, 3) for k, v in ctx.stats()["stage_ms"].items()}}
+        # -- strong_1h
+        n1h = 900
+        mine = list(range(rank, n1h, world))
+        base48 = make_frames(min(len(mine), 64), FRAME_SECONDS, seed=777 + rank, sample_rate=48000)
+        f48 = [base48[i % len(base48)] for i in range(len(mine))]
+        S48 = f48[0].shape[1]
+        h48 = torch.from_numpy(np.stack(f48)).pin_memory()
+        d48 = h48.to("cuda", non_blocking=True)
+        torch.cuda.synchronize()
+        lay48 = [(i * CHANNELS * S48, S48, CHANNELS, S48) for i in range(len(mine))]
+        ms = timed_dev(d48, lay48, params)
+        extras["strong_1h"] = {"config": "BASELINE.json configs[4]: one synthetic 1-hour 48 kHz stereo stream = 900 frames of 4 s "
+                                         "(N=96,000 chunks, K=%d, %d-bit), frames split over %d rank(s)" % (K, args.bits, world),
+                               "scaling": "strong", "frames_per_rank": len(mine), "value": 3600.0 / (ms * 1e-3), "unit": UNIT,
+                               "ms_per_step": ms}
+        del d48, h48
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         cf = make_frames(cores, args.cpu_sample_seconds, seed=4321)
-        dt, cres = cpu_encode_sample(cf, K, args.bits, cores)
+        dt, cres = cpu_encode_sample(cf, K, args.bits, cores, args.cpu_search)
         cpu = {"value": sum(f.shape[1] for f in cf) / SAMPLE_RATE / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} frames x {args.cpu_sample_seconds:g} s of the same synthetic audio (N={cres[0].N} "
-                         f"chunks/frame, K={K}), one frame per host thread, {dt:.1f} s wall; online passes "
-                         f"{[r.passes for r in cres]}; the port searches every centroid (vectorised) where the "
-                         f"reference walks an ANN kd-tree, same results"}
+               "sample": cpu_sample_text(cores, args.cpu_sample_seconds, cres, K, args.cpu_search, f", {dt:.1f} s wall")}
 
     if rank == 0:
         line = {
@@ -378,7 +473,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, F, FRAME_SECONDS),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "lloyd_mode": lloyd,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "parity_check": parity, "lloyd_mode": lloyd, **extras,
             "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
             "online_passes": {"min": min(passes), "median": statistics.median(passes), "max": max(passes)},
             "chunks_per_frame_N": Ns[0],

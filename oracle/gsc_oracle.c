@@ -555,6 +555,302 @@ int gsc_ref_knn_scan_reduce(const float *X, int N, int D, float *centroids,
                                            max_passes, 1, labels, err_out);
 }
 
+/* ------------------------------------------------------------------ */
+/* ANN 1.1.2 kd-tree (D. Mount, S. Arya), restated from its published   */
+/* source (kd_tree.cpp, kd_split.cpp, kd_util.cpp, kd_search.cpp): the  */
+/* structure KNNScanReduce really searches.  enc:729 builds it over the */
+/* centroid rows (bucket size 1, ANN_KD_STD) at the start of every pass */
+/* and enc:733 asks for the nearest point (annkSearch, k = 1, eps = 0). */
+/* ANN keeps the caller's row pointers (no copy): leaf   */
+/* distances read the LIVE rows, which enc:736-740 moves between        */
+/* queries, while splitting planes and bounding boxes date from the     */
+/* start of the pass.  ANNcoord = ANNdist = float in the shipped DLL.   */
+/* Ties keep the first point VISITED (ANNmin_k::insert), not the lowest */
+/* index.  ANN.dll's source is not in the reference tree: third-party,  */
+/* version string "ANN Version 1.1.2".                                  */
+/* ------------------------------------------------------------------ */
+static float knnfit_epsilon(int bits, double law);
+static inline int same_value_f(float a, float b, float eps);
+typedef struct ann_node { int cd; float cv, lo_b, hi_b; int lo, hi; int pt; } ann_node;   /* pt >= 0: leaf; -2: trivial */
+typedef struct ann_tree {
+    const float *pts; int dim, n;
+    ann_node *nodes; int n_nodes, root;
+    float *bb_lo, *bb_hi;
+    int32_t *pidx;
+} ann_tree;
+
+#define ANN_PA(t, i, d) ((t)->pts[(size_t)(t)->pidx[(i)] * (t)->dim + (d)])
+
+static int ann_max_spread(const ann_tree *t, int off, int n)        /* kd_util.cpp annMaxSpread / annSpread */
+{
+    int max_dim = 0;
+    float max_spr = 0;
+    if (n == 0) return max_dim;
+    for (int d = 0; d < t->dim; ++d) {
+        float mn = ANN_PA(t, off, d), mx = mn;
+        for (int i = 1; i < n; ++i) {
+            float c = ANN_PA(t, off + i, d);
+            if (c < mn) mn = c; else if (c > mx) mx = c;
+        }
+        float spr = mx - mn;
+        if (spr > max_spr) { max_spr = spr; max_dim = d; }
+    }
+    return max_dim;
+}
+
+static void ann_median_split(ann_tree *t, int off, int n, int d, float *cv, int n_lo)   /* kd_util.cpp annMedianSplit */
+{
+#define PAV(i) ANN_PA(t, off + (i), d)
+#define PASWAP(a, b) do { int32_t tmp_ = t->pidx[off + (a)]; t->pidx[off + (a)] = t->pidx[off + (b)]; t->pidx[off + (b)] = tmp_; } while (0)
+    int l = 0, r = n - 1;
+    while (l < r) {
+        int i = (r + l) / 2, k;
+        if (PAV(i) > PAV(r)) PASWAP(i, r);
+        PASWAP(l, i);
+        float c = PAV(l);
+        i = l; k = r;
+        for (;;) {
+            while (i < r && PAV(++i) < c) ;      /* (bounds added: NaN rows must not run off the array) */
+            while (k > l && PAV(--k) > c) ;
+            if (i < k) PASWAP(i, k); else break;
+        }
+        PASWAP(l, k);
+        if (k > n_lo) r = k - 1;
+        else if (k < n_lo) l = k + 1;
+        else break;
+    }
+    if (n_lo > 0) {
+        float c = PAV(0);
+        int k = 0;
+        for (int i = 1; i < n_lo; ++i) if (PAV(i) > c) { c = PAV(i); k = i; }
+        PASWAP(n_lo - 1, k);
+    }
+    *cv = (float)(((double)PAV(n_lo - 1) + (double)PAV(n_lo)) / 2.0);
+#undef PAV
+#undef PASWAP
+}
+
+static int ann_build_rec(ann_tree *t, int off, int n)               /* kd_tree.cpp rkd_tree, bucket size 1 */
+{
+    int id = t->n_nodes++;
+    ann_node *nd = &t->nodes[id];
+    if (n <= 1) { nd->pt = (n == 0) ? -2 : t->pidx[off]; nd->lo = nd->hi = -1; return id; }
+    int cd = ann_max_spread(t, off, n), n_lo = n / 2;                /* kd_split.cpp kd_split */
+    float cv;
+    ann_median_split(t, off, n, cd, &cv, n_lo);
+    float lv = t->bb_lo[cd], hv = t->bb_hi[cd];
+    t->bb_hi[cd] = cv;
+    int lo = ann_build_rec(t, off, n_lo);
+    t->bb_hi[cd] = hv;
+    t->bb_lo[cd] = cv;
+    int hi = ann_build_rec(t, off + n_lo, n - n_lo);
+    t->bb_lo[cd] = lv;
+    nd = &t->nodes[id];
+    nd->pt = -1; nd->cd = cd; nd->cv = cv; nd->lo_b = lv; nd->hi_b = hv; nd->lo = lo; nd->hi = hi;
+    return id;
+}
+
+static void ann_build(ann_tree *t, const float *pts, int n, int dim)
+{
+    t->pts = pts; t->n = n; t->dim = dim;
+    t->nodes = (ann_node *)malloc(sizeof(ann_node) * (size_t)(2 * n + 2));
+    t->n_nodes = 0;
+    t->pidx = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    t->bb_lo = (float *)malloc(sizeof(float) * dim * 2);
+    t->bb_hi = t->bb_lo + dim;
+    for (int i = 0; i < n; ++i) t->pidx[i] = i;
+    for (int d = 0; d < dim; ++d) {                                  /* annEnclRect */
+        float lo = pts[d], hi = pts[d];
+        for (int i = 0; i < n; ++i) {
+            float c = pts[(size_t)i * dim + d];
+            if (c < lo) lo = c; else if (c > hi) hi = c;
+        }
+        t->bb_lo[d] = lo; t->bb_hi[d] = hi;
+    }
+    t->root = ann_build_rec(t, 0, n);
+}
+static void ann_free(ann_tree *t) { free(t->nodes); free(t->pidx); free(t->bb_lo); }
+
+typedef struct ann_query { const float *q; float best; int idx; long visited; } ann_query;
+
+static void ann_search_rec(const ann_tree *t, int id, float box_dist, ann_query *s)   /* kd_search.cpp */
+{
+    const ann_node *nd = &t->nodes[id];
+    if (nd->pt != -1) {                                              /* ANNkd_leaf::ann_search */
+        if (nd->pt < 0) return;
+        const float *pp = t->pts + (size_t)nd->pt * t->dim;
+        float min_dist = s->best, dist = 0;
+        int d;
+        for (d = 0; d < t->dim; ++d) {
+            float tt = s->q[d] - pp[d];
+            float m = tt * tt;
+            dist = dist + m;
+            if (dist > min_dist) break;
+        }
+        if (d >= t->dim && s->idx < 0) { s->best = dist; s->idx = nd->pt; }             /* first point */
+        else if (d >= t->dim && dist < s->best) { s->best = dist; s->idx = nd->pt; }    /* equal keys keep the first visited */
+        s->visited++;
+        return;
+    }
+    float cut_diff = s->q[nd->cd] - nd->cv;                          /* ANNkd_split::ann_search */
+    if (cut_diff < 0) {
+        ann_search_rec(t, nd->lo, box_dist, s);
+        float box_diff = nd->lo_b - s->q[nd->cd];
+        if (box_diff < 0) box_diff = 0;
+        box_dist = box_dist + (cut_diff * cut_diff - box_diff * box_diff);
+        if ((double)box_dist * 1.0 < (double)s->best) ann_search_rec(t, nd->hi, box_dist, s);
+    } else {
+        ann_search_rec(t, nd->hi, box_dist, s);
+        float box_diff = s->q[nd->cd] - nd->hi_b;
+        if (box_diff < 0) box_diff = 0;
+        box_dist = box_dist + (cut_diff * cut_diff - box_diff * box_diff);
+        if ((double)box_dist * 1.0 < (double)s->best) ann_search_rec(t, nd->lo, box_dist, s);
+    }
+}
+
+static int ann_search1(const ann_tree *t, const float *q, float *dist_out, long *visited)
+{
+    float bd = 0;                                                    /* annBoxDistance */
+    for (int d = 0; d < t->dim; ++d) {
+        if (q[d] < t->bb_lo[d]) { float tt = t->bb_lo[d] - q[d]; bd = bd + tt * tt; }
+        else if (q[d] > t->bb_hi[d]) { float tt = q[d] - t->bb_hi[d]; bd = bd + tt * tt; }
+    }
+    ann_query s = { q, 3.40282346638528860e+38f, -1, 0 };
+    ann_search_rec(t, t->root, bd, &s);
+    if (dist_out) *dist_out = s.best;
+    if (visited) *visited += s.visited;
+    return s.idx;
+}
+
+/* k nearest points, ascending by distance; equal keys keep the order they were visited in (ANNmin_k::insert).
+ * enc:952 calls annkPriSearch, which visits the cells in another order than this (standard) search; for eps = 0
+ * both return the same k distances, and the same rows wherever the k-th distance is not tied. */
+typedef struct ann_kquery { const float *q; int k, n; float *key; int *idx; } ann_kquery;
+
+static void ann_ksearch_rec(const ann_tree *t, int id, float box_dist, ann_kquery *s)
+{
+    const ann_node *nd = &t->nodes[id];
+    if (nd->pt != -1) {
+        if (nd->pt < 0) return;
+        const float *pp = t->pts + (size_t)nd->pt * t->dim;
+        float min_dist = (s->n == s->k) ? s->key[s->k - 1] : 3.40282346638528860e+38f, dist = 0;
+        int d;
+        for (d = 0; d < t->dim; ++d) {
+            float tt = s->q[d] - pp[d];
+            float m = tt * tt;
+            dist = dist + m;
+            if (dist > min_dist) break;
+        }
+        if (d >= t->dim) {                                       /* ANNmin_k::insert */
+            int i;
+            for (i = s->n; i > 0; --i) {
+                if (s->key[i - 1] > dist) { if (i < s->k) { s->key[i] = s->key[i - 1]; s->idx[i] = s->idx[i - 1]; } }
+                else break;
+            }
+            if (i < s->k) { s->key[i] = dist; s->idx[i] = nd->pt; }
+            if (s->n < s->k) s->n++;
+        }
+        return;
+    }
+    float cut_diff = s->q[nd->cd] - nd->cv;
+    int near_c = (cut_diff < 0) ? nd->lo : nd->hi, far_c = (cut_diff < 0) ? nd->hi : nd->lo;
+    ann_ksearch_rec(t, near_c, box_dist, s);
+    float box_diff = (cut_diff < 0) ? nd->lo_b - s->q[nd->cd] : s->q[nd->cd] - nd->hi_b;
+    if (box_diff < 0) box_diff = 0;
+    box_dist = box_dist + (cut_diff * cut_diff - box_diff * box_diff);
+    float kth = (s->n == s->k) ? s->key[s->k - 1] : 3.40282346638528860e+38f;
+    if ((double)box_dist * 1.0 < (double)kth) ann_ksearch_rec(t, far_c, box_dist, s);
+}
+
+/* enc:915-965 the way the binary runs it: ANN kd-tree over the 4R variant rows (enc:945), 64 nearest rows per
+ * chunk (enc:952), lowest index within epsilon of the nearest (enc:954-958).  Same answers as gsc_ref_knnfit's
+ * `best` wherever at most 64 rows lie inside the band. */
+void gsc_ref_knnfit_kdtree(const int16_t *dict, const uint8_t *datten, int R, int cs, int bits, int divider,
+                           const double *raw, int N, int32_t *best, int32_t *use)
+{
+    double law = 1.0 / (double)divider;
+    int M = R * 4;
+    float *V = (float *)malloc(sizeof(float) * (size_t)M * cs);
+    gsc_ref_knnfit_variants(dict, datten, R, cs, bits, divider, V);
+    ann_tree t;
+    ann_build(&t, V, M, cs);
+    float eps = knnfit_epsilon(bits, law);
+    float key[GSC_BUCKET]; int idx[GSC_BUCKET]; float q[64];
+    if (use) memset(use, 0, sizeof(int32_t) * R);
+    int kk = M < GSC_BUCKET ? M : GSC_BUCKET;
+    for (int i = 0; i < N; ++i) {
+        for (int j = 0; j < cs; ++j) q[j] = (float)raw[(size_t)i * cs + j];
+        float bd = 0;
+        for (int d = 0; d < cs; ++d) {
+            if (q[d] < t.bb_lo[d]) { float tt = t.bb_lo[d] - q[d]; bd = bd + tt * tt; }
+            else if (q[d] > t.bb_hi[d]) { float tt = q[d] - t.bb_hi[d]; bd = bd + tt * tt; }
+        }
+        ann_kquery s = { q, kk, 0, key, idx };
+        ann_ksearch_rec(&t, t.root, bd, &s);
+        float a = sqrtf(key[0] / (float)cs);
+        int b = idx[0];
+        for (int j = 1; j < s.n; ++j)
+            if (same_value_f(a, sqrtf(key[j] / (float)cs), eps) && idx[j] < b) b = idx[j];
+        best[i] = b;
+        if (use) use[b >> 2]++;
+    }
+    ann_free(&t);
+    free(V);
+}
+
+/* enc:699-765 with the search the binary performs: an ANN kd-tree over the LIVE centroid rows, rebuilt at the
+ * start of every pass (enc:729, 759).  mode 0: the tree as ANN uses it (planes and boxes go stale while the pass
+ * moves the rows; ties to the first point visited) -- the closest this restatement gets to the shipped encoder.
+ * stats (optional, 2 longs): points visited, queries whose answer differs from the exact nearest centroid. */
+int gsc_ref_knn_scan_reduce_kdtree(const float *X, int N, int D, float *centroids, int K, int precision,
+                                   int max_passes, int32_t *labels, double *err_out, long *stats)
+{
+    int32_t *cnts[2];
+    cnts[0] = (int32_t *)malloc(sizeof(int32_t) * K);
+    cnts[1] = (int32_t *)malloc(sizeof(int32_t) * K);
+    for (int j = 0; j < K; ++j) { cnts[0][j] = 1; cnts[1][j] = 1; }
+    const double tol = int_power10_neg(precision);
+    int iter = 0;
+    double err = 3.40282346638528860e+38, prevErr;
+    long visited = 0, inexact = 0;
+    float *acc = stats ? (float *)malloc(sizeof(float) * K) : NULL;
+    do {
+        prevErr = err;
+        err = 0;
+        const int odd = iter & 1;
+        ann_tree t;
+        ann_build(&t, centroids, K, D);                                /* enc:729 */
+        for (int i = 0; i < N; ++i) {
+            const float *x = X + (size_t)i * D;
+            float best;
+            int bi = ann_search1(&t, x, &best, &visited);              /* enc:733 */
+            if (bi < 0) { bi = 0; best = 0; }
+            if (stats) {            /* how often do the stale planes / the tie order change the answer? */
+                float bd = INFINITY; int be = 0;
+                for (int c = 0; c < K; ++c) {
+                    float d = 0;
+                    for (int k = 0; k < D; ++k) { float tt = x[k] - centroids[(size_t)c * D + k]; d = d + tt * tt; }
+                    if (d < bd) { bd = d; be = c; }
+                }
+                inexact += (be != bi);
+            }
+            float rate = (float)(1.0 / sqrt((double)cnts[!odd][bi]));  /* enc:735 */
+            float *c = centroids + (size_t)bi * D;
+            for (int k = 0; k < D; ++k) { float v = x[k] - c[k]; float m = v * rate; c[k] = c[k] + m; }   /* enc:736-740 */
+            labels[i] = bi;
+            err += (double)sqrtf(best / (float)D);                     /* enc:743 */
+            cnts[odd][bi] += 1;
+        }
+        for (int j = 0; j < K; ++j) cnts[!odd][j] = 1;
+        ann_free(&t);                                                  /* enc:759 */
+        ++iter;
+    } while (!(same_value_d(err, prevErr, tol) || iter >= max_passes));
+    if (err_out) *err_out = err;
+    if (stats) { stats[0] = visited; stats[1] = inexact; }
+    free(cnts[0]); free(cnts[1]); free(acc);
+    return iter;
+}
+
 /* Plain batch Lloyd (the 1e-4 centroid contract of BASELINE.json).  There is no
  * Lloyd in the reference to follow (enc:824 calls yakmo with maxIter = 0), so the
  * arithmetic is ours: member rows are accumulated in Double and the mean is
@@ -854,8 +1150,12 @@ int gsc_ref_encode_frame(const int16_t *pcm, int64_t stride, int C, int S,
             out->passes = p->lloyd_iters;
         } else {
             int batch = (p->kmeans_mode == 2) ? p->batch : 1;
-            out->passes = gsc_ref_knn_scan_reduce_batched(feat, N, D, cen, K, p->precision,
-                                                          p->max_passes, batch, labels, &out->err);
+            if (p->kmeans_mode == 3)
+                out->passes = gsc_ref_knn_scan_reduce_kdtree(feat, N, D, cen, K, p->precision,
+                                                             p->max_passes, labels, &out->err, NULL);
+            else
+                out->passes = gsc_ref_knn_scan_reduce_batched(feat, N, D, cen, K, p->precision,
+                                                              p->max_passes, batch, labels, &out->err);
         }
         R = K;
         dict = (int16_t *)malloc(sizeof(int16_t) * (size_t)R * cs);
@@ -876,7 +1176,12 @@ int gsc_ref_encode_frame(const int16_t *pcm, int64_t stride, int C, int S,
     int32_t *best = (int32_t *)malloc(sizeof(int32_t) * N);
     int32_t *use = (int32_t *)malloc(sizeof(int32_t) * R);
     int32_t *band = (int32_t *)malloc(sizeof(int32_t) * N);
-    if (p->band_all) {
+    if (p->kmeans_mode == 3 && !p->band_all) {
+        gsc_ref_knnfit_kdtree(dict, datten, R, cs, bits, divider, raw, N, best, use);
+        int32_t *b2 = (int32_t *)malloc(sizeof(int32_t) * N);
+        for (int j = 0; j < N; ++j) band[j] = 0;
+        free(b2);
+    } else if (p->band_all) {
         int32_t *b64 = (int32_t *)malloc(sizeof(int32_t) * N);
         gsc_ref_knnfit(dict, datten, R, cs, bits, divider, raw, N, b64, NULL, band, best, NULL);
         memset(use, 0, sizeof(int32_t) * R);

@@ -82,6 +82,16 @@ int gsc_ref_knn_scan_reduce_batched(const float *X, int N, int D,
                                     int max_passes, int batch,
                                     int32_t *labels, double *err_out);
 
+/* enc:699-765 searched the way the binary searches it: ANN 1.1.2 kd-tree (bucket 1, ANN_KD_STD) over the live
+ * centroid rows, rebuilt every pass.  stats (optional): [0] points visited, [1] queries whose answer is not the
+ * exact nearest centroid (lowest index). */
+int gsc_ref_knn_scan_reduce_kdtree(const float *X, int N, int D, float *centroids, int K, int precision,
+                                   int max_passes, int32_t *labels, double *err_out, long *stats);
+
+/* enc:915-965 through the same kd-tree (64-NN, epsilon band); best == gsc_ref_knnfit's wherever overfull == 0. */
+void gsc_ref_knnfit_kdtree(const int16_t *dict, const uint8_t *datten, int R, int cs, int bits, int divider,
+                           const double *raw, int N, int32_t *best, int32_t *use);
+
 /* Plain batch Lloyd: `iters` x (assign to nearest, lowest index on ties;
  * mean in float, point order).  Empty clusters keep their centroid. */
 void gsc_ref_lloyd(const float *X, int N, int D, float *centroids, int K,
@@ -143,7 +153,9 @@ typedef struct gsc_ref_params {
     int chunks_per_frame;  /* -cpf default 4096  enc:1505 */
     int precision;         /* -pr  default 3     enc:1503 */
     int max_passes;        /* CMaxIterations = 100, enc:703 */
-    int kmeans_mode;       /* 0 online (reference), 1 lloyd, 2 online batched */
+    int kmeans_mode;       /* 0 online, exact search on the live centroids (the library's contract); 1 lloyd;
+                              2 online batched; 3 online through an ANN-1.1.2-style kd-tree rebuilt per pass
+                              (planes go stale while the pass moves the rows: what the shipped binary does) */
     int lloyd_iters;       /* mode 1 */
     int batch;             /* mode 2 */
     double frame_length_ms;/* -fl  default 4000  enc:1501 */

@@ -174,6 +174,20 @@ def knn_scan_reduce(X, centroids, precision=3, max_passes=100, batch=1):
     return cen, labels, it, err.value
 
 
+def knn_scan_reduce_kdtree(X, centroids, precision=3, max_passes=100, stats=False):
+    """enc:699-765 through the ANN-style kd-tree (rebuilt per pass, live rows, stale planes).
+    -> centroids, labels, passes, err[, (points visited, answers that are not the exact nearest centroid)]"""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    cen = np.array(centroids, dtype=np.float32, order="C", copy=True)
+    N, D = X.shape
+    labels = np.zeros(N, np.int32)
+    err = C.c_double(0)
+    st = (C.c_long * 2)(0, 0)
+    it = lib().gsc_ref_knn_scan_reduce_kdtree(_p(X, C.c_float), N, D, _p(cen, C.c_float), cen.shape[0], precision,
+                                              max_passes, _p(labels, C.c_int32), C.byref(err), st if stats else None)
+    return (cen, labels, it, err.value, (st[0], st[1])) if stats else (cen, labels, it, err.value)
+
+
 def lloyd(X, centroids, iters):
     X = np.ascontiguousarray(X, dtype=np.float32)
     cen = np.array(centroids, dtype=np.float32, order="C", copy=True)
@@ -248,6 +262,19 @@ def knnfit(dic, datten, raw, bits=12, divider=6):
                                _p(out["use"], C.c_int32), _p(out["band"], C.c_int32),
                                _p(out["best_all"], C.c_int32), _p(out["dbl_diff"], C.c_int32))
     out["epsilon"] = float(eps)
+    return out
+
+
+def knnfit_kdtree(dic, datten, raw, bits=12, divider=6):
+    """KNNFit through the ANN-style kd-tree (64 nearest rows, epsilon band) -> dict(best, use)"""
+    dic = np.ascontiguousarray(dic, dtype=np.int16)
+    datten = np.ascontiguousarray(datten, dtype=np.uint8)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    R, cs = dic.shape
+    N = raw.shape[0]
+    out = dict(best=np.zeros(N, np.int32), use=np.zeros(R, np.int32))
+    lib().gsc_ref_knnfit_kdtree(_p(dic, C.c_int16), _p(datten, C.c_uint8), R, cs, bits, divider, _p(raw, C.c_double), N,
+                                _p(out["best"], C.c_int32), _p(out["use"], C.c_int32))
     return out
 
 

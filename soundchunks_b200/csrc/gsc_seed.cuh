@@ -20,7 +20,7 @@
 //    windows are re-summarised (one warp each).  One warp then CHAINS the windows in order: a summary is used iff
 //    the actual entry exponent equals the predicted one and S - neg >= 2^23, S + pos < 2^24 (every partial sum
 //    stays in the binade, so the composition IS the sequential result); any other window (a binade crossing inside
-//    it, ~10 per step) is evaluated element by element by the warp with the exact round scheme of gsc_warp_chain.
+//    it, ~10 per step) is added up element by element (gsc_warp_chain).
 //    The chain yields the exact entry sum of every window and the exact total obj.
 //  * lower_bound follows std::lower_bound's probes exactly: a probe in a window without negative elements is
 //    decided from the window's entry / exit sums when the target lies outside them (the sums are monotone there);
@@ -86,126 +86,54 @@ __device__ __forceinline__ void gsc_load8(const float *a, int j0, int n, float (
 }
 
 // ---------------------------------------------------------------------------
-// Exact sequential float sum  run := fl(run + a[j]),  j = 0..n-1  (n <= 256), evaluated by ONE WARP.
-// out (shared memory or null): out[j] = the sum after element j.  All 32 lanes call with the same arguments.
-// Rounds: within the binade of the running sum the elements are integer functions (see above) and a warp scan
-// certifies everything up to the first element that would leave the binade; that element is added with one real
-// float addition and the next round continues behind it.  A zero running sum skips zero elements; when a round
-// makes little progress (the first elements of a frame, where the sum doubles every few elements) the next 32
-// elements are added one after the other.
+// Exact sequential float sum  run := fl(run + a[j]),  j = 0..n-1  (n <= 256) of ONE window, called by a whole warp
+// with the same arguments: the warp stages the window in shared memory with one coalesced load, lane 0 adds the
+// elements one after the other (a 256-long FADD chain costs about what two certified scan rounds would, with
+// none of their special cases) and the sum is handed to every lane.  prefix: buf[j] := the sum after element j.
 // ---------------------------------------------------------------------------
-__device__ float gsc_warp_chain(const float *a, int n, float run, float *out) {
+__device__ __forceinline__ float gsc_warp_chain(const float *a, int n, float run, float *buf, bool prefix) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, j0 = lane * 8;
+    const int lane = threadIdx.x & 31;
     float v[8];
-    gsc_load8(a, j0, n, v);
-    int pos = 0;
-    while (pos < n) {
-        const unsigned rb = __float_as_uint(run);
-        const int E0 = (int)((rb >> 23) & 0xffu);
-        int viol = n;       // first index >= pos this lane cannot certify
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = 0.0f;
-        if (run == 0.0f) {
-            // 0 + a = a exactly: zero elements leave the sum at +0 (fl(+0 + -0) = +0)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int j = j0 + e;
-                if (j >= pos && j < n && viol == n && v[e] != 0.0f) viol = j;
-            }
-        } else if ((rb >> 31) == 0u && E0 >= 24 && E0 <= 250) {
-            const int Sm = (int)((rb & 0x7fffffu) | 0x800000u);
-            const float sc = __uint_as_float((unsigned)(277 - E0) << 23);    // 1 / ulp = 2^(150 - E0)
-            const float huge = __uint_as_float((unsigned)(E0 + 2) << 23);    // 4 * 2^(E0 - 127)
-            int I[8], cls[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int j = j0 + e;
-                I[e] = 0; cls[e] = 0;
-                if (j >= pos && j < n) gsc_classify(v[e], sc, huge, I[e], cls[e]);
-            }
-            int f0 = 0, f1 = 1;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { f0 = gsc_pf_step(f0, I[e], cls[e]); f1 = gsc_pf_step(f1, I[e], cls[e]); }
-            f1 -= 1;
-            int s0 = f0, s1 = f1;   // inclusive scan over the lanes
-#pragma unroll
-            for (int of = 1; of < 32; of <<= 1) {
-                const int p0 = __shfl_up_sync(FULL, s0, of), p1 = __shfl_up_sync(FULL, s1, of);
-                if (lane >= of) { int q0 = p0, q1 = p1; gsc_pf_compose(q0, q1, s0, s1); s0 = q0; s1 = q1; }
-            }
-            int x0 = __shfl_up_sync(FULL, s0, 1), x1 = __shfl_up_sync(FULL, s1, 1);
-            if (lane == 0) { x0 = 0; x1 = 0; }
-            int S = Sm + ((Sm & 1) ? x1 : x0);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int j = j0 + e;
-                if (j >= pos && j < n && viol == n) {
-                    const int t = S + I[e];
-                    const int Sn = t + ((cls[e] & 1) | ((cls[e] >> 1) & t & 1));
-                    if (cls[e] >= 4 || t < (1 << 23) || Sn >= (1 << 24) || S < (1 << 23) || S >= (1 << 24)) viol = j;
-                    else { S = Sn; o[e] = __uint_as_float(((unsigned)E0 << 23) | ((unsigned)Sn & 0x7fffffu)); }
-                }
-            }
-        } else {
-            viol = pos;     // negative / denormal / non-finite running sum: one real addition
+    gsc_load8(a, lane * 8, n, v);
+    __syncwarp();
+    *reinterpret_cast<float4 *>(buf + lane * 8) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4 *>(buf + lane * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    __syncwarp();
+    float r = run;
+    if (lane == 0) {
+        const int n8 = n & ~7;
+        for (int j = 0; j < n8; j += 8) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(buf + j), x1 = *reinterpret_cast<const float4 *>(buf + j + 4);
+            float4 y0, y1;
+            r = r + x0.x; y0.x = r; r = r + x0.y; y0.y = r; r = r + x0.z; y0.z = r; r = r + x0.w; y0.w = r;
+            r = r + x1.x; y1.x = r; r = r + x1.y; y1.y = r; r = r + x1.z; y1.z = r; r = r + x1.w; y1.w = r;
+            if (prefix) { *reinterpret_cast<float4 *>(buf + j) = y0; *reinterpret_cast<float4 *>(buf + j + 4) = y1; }
         }
-        viol = (int)__reduce_min_sync(FULL, (unsigned)viol);
-        // elements [pos, viol) are final
-        float mine_before = 0.0f, mine_add = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int j = j0 + e;
-            if (out && j >= pos && j < viol) out[j] = o[e];
-            if (j == viol - 1) mine_before = o[e];
-            if (j == viol) mine_add = v[e];
-        }
-        float before = run;
-        if (viol > pos) before = __shfl_sync(FULL, mine_before, (viol - 1) >> 3);
-        const int progressed = viol - pos;
-        if (viol < n) {
-            const float addend = __shfl_sync(FULL, mine_add, viol >> 3);
-            run = before + addend;      // the one real float addition
-            if (out && lane == 0) out[viol] = run;
-            pos = viol + 1;
-        } else {
-            run = before;
-            pos = n;
-        }
-        if (progressed < 24 && pos < n && run != 0.0f) {
-            // little progress: the next (up to) 32 elements one after the other
-            const int cnt = min(32, n - pos);
-            const float val = (lane < cnt) ? a[pos + lane] : 0.0f;
-            float rr = run, mine = 0.0f;
-            for (int l = 0; l < cnt; ++l) {
-                const float x = __shfl_sync(FULL, val, l);
-                rr = rr + x;
-                if (lane == l) mine = rr;
-            }
-            if (out && lane < cnt) out[pos + lane] = mine;
-            run = rr;
-            pos += cnt;
-        }
-        __syncwarp();
+        for (int j = n8; j < n; ++j) { r = r + buf[j]; if (prefix) buf[j] = r; }
     }
-    return run;
+    __syncwarp();
+    return __shfl_sync(FULL, r, 0);
 }
 
 // ---------------------------------------------------------------------------
-// Summary of one window (elements a[0..n), n <= 256) under the exponent field e0 of its entry sum, by one warp.
-// Lane 0 returns everything: (f0, f1, neg, pos) and the flags; e0 outside 24..250 yields flags only.
+// Summary of one window (elements a[0..n), n <= 256) under the exponent field e0 of its entry sum, by one warp:
+// (f0, f1, neg, pos) and flags = e0 << 8 | GSC_SF_*; e0 outside 26..250 yields GSC_SF_BAD (no summary).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void gsc_window_summary(const float *a, int n, int e0, int4 &sum, int &flags) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     float v[8];
     gsc_load8(a, lane * 8, n, v);
+    const bool valid = e0 >= 26 && e0 <= 250;
+    // a negative element below a quarter ulp of binade e0 never changes a sum that is >= 2^(e0-127): the prefix sums
+    // stay monotone (fl(S ulp - t) = S ulp for t <= ulp/4, also at S = 2^23 where the spacing below halves)
+    const float harmless = valid ? __uint_as_float((unsigned)(e0 - 25) << 23) : 0.0f;
     bool bad = false, hasneg = false;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { hasneg |= (v[e] < 0.0f); bad |= !(fabsf(v[e]) < 3.0e38f); }
+    for (int e = 0; e < 8; ++e) { hasneg |= (v[e] < 0.0f) && !(fabsf(v[e]) < harmless); bad |= !(fabsf(v[e]) < 3.0e38f); }
     int f0 = 0, f1 = 0, neg = 0, pos = 0;
-    if (e0 >= 24 && e0 <= 250) {
+    if (valid) {
         const float sc = __uint_as_float((unsigned)(277 - e0) << 23);
         const float huge = __uint_as_float((unsigned)(e0 + 2) << 23);
         int g0 = 0, g1 = 1;
@@ -233,7 +161,7 @@ __device__ __forceinline__ void gsc_window_summary(const float *a, int n, int e0
     }
     const bool anybad = __any_sync(FULL, bad), anyneg = __any_sync(FULL, hasneg);
     sum = make_int4(f0, f1, neg, pos);
-    flags = (anybad ? GSC_SF_BAD : 0) | (anyneg ? GSC_SF_NEG : 0);
+    flags = ((valid ? e0 : 0) << 8) | (anybad ? GSC_SF_BAD : 0) | (anyneg ? GSC_SF_NEG : 0);
 }
 
 // ---------------------------------------------------------------------------
@@ -328,25 +256,27 @@ __global__ void __launch_bounds__(512) k_seed_prep(const GscFrame *__restrict__ 
 // ---------------------------------------------------------------------------
 __host__ __device__ inline size_t gsc_seed2_smem(int N) {
     const size_t nw = (size_t)(N + GSC_SW - 1) / GSC_SW;
-    return 4 * ((size_t)(N + 31) / 32) + 4 * (nw + 1) + 4 * nw + 4 * nw + 4 * nw + 4 * ((nw + 31) / 32) + ((nw + 3) & ~(size_t)3) + 4 * GSC_SW + 64;
+    return 4 * ((size_t)(N + 31) / 32) + 4 * (nw + 1) + 7 * 4 * nw + 4 * ((nw + 31) / 32) + 4 * GSC_SW + 64;
 }
 
+__device__ __forceinline__ float gsc_mkf(int e, int S) { return __uint_as_float(((unsigned)e << 23) | ((unsigned)S & 0x7fffffu)); }
+
 template <int D>
-__global__ void __launch_bounds__(GSC_SEED2_T) k_seed2(const GscFrame *__restrict__ frames,
-                                                       const float *__restrict__ X,     // [sumN][D] original order
-                                                       const float *__restrict__ Xs,    // [sumN][D] bucketed order
-                                                       const float *__restrict__ pns,   // [sumN] norms, bucketed order
-                                                       const int *__restrict__ perm,    // [sumN] bucketed -> original
-                                                       const float *__restrict__ blo, const float *__restrict__ bhi,
-                                                       int init_type,
-                                                       float *__restrict__ ups,         // [sumN] distances, bucketed order
-                                                       float *__restrict__ up,          // [sumN] distances, original order
-                                                       int *__restrict__ sid,           // [sumN] seed cell, original order
-                                                       int4 *__restrict__ wsum,         // [windows] summaries
-                                                       int *__restrict__ seeds,         // [F][Kmax] or null
-                                                       float *__restrict__ cen,         // [F][Kmax][D] seeds out
-                                                       float *__restrict__ cnorm,       // [F][Kmax]
-                                                       int Kmax, unsigned long long *__restrict__ sdbg) {
+__global__ void __launch_bounds__(GSC_SEED2_T, 2) k_seed2(const GscFrame *__restrict__ frames,
+                                                          const float *__restrict__ X,     // [sumN][D] original order
+                                                          const float *__restrict__ Xs,    // [sumN][D] bucketed order
+                                                          const float *__restrict__ pns,   // [sumN] norms, bucketed order
+                                                          const int *__restrict__ perm,    // [sumN] bucketed -> original
+                                                          const float *__restrict__ blo, const float *__restrict__ bhi,
+                                                          int init_type,
+                                                          float *__restrict__ ups,         // [sumN] distances, bucketed order
+                                                          float *__restrict__ up,          // [sumN] distances, original order
+                                                          int *__restrict__ sid,           // [sumN] seed cell, original order
+                                                          int4 *__restrict__ wsum,         // [windows] summaries
+                                                          int *__restrict__ seeds,         // [F][Kmax] or null
+                                                          float *__restrict__ cen,         // [F][Kmax][D] seeds out
+                                                          float *__restrict__ cnorm,       // [F][Kmax]
+                                                          int Kmax, unsigned long long *__restrict__ sdbg) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int T = GSC_SEED2_T, W = T / 32;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -361,25 +291,28 @@ __global__ void __launch_bounds__(GSC_SEED2_T) k_seed2(const GscFrame *__restric
     const int nw = (N + GSC_SW - 1) / GSC_SW;
     unsigned *chosen = reinterpret_cast<unsigned *>(smraw);
     float *entry = reinterpret_cast<float *>(chosen + (N + 31) / 32);      // [nw+1]: entry[w] = sum before window w, entry[nw] = obj
-    int *wexp = reinterpret_cast<int *>(entry + nw + 1);                   // [nw] exponent the summary was made for (-1: none)
-    float *bmax = reinterpret_cast<float *>(wexp + nw);                    // [nw] >= every current distance of the block (>= 0)
-    int *list = reinterpret_cast<int *>(bmax + nw);                        // [nw]
+    int *wexp = reinterpret_cast<int *>(entry + nw + 1);                   // [nw] exponent the NEXT summary is to be made for (-1: none)
+    int *wfl = wexp + nw;                                                  // [nw] exponent the summary was made for << 8 | GSC_SF_*
+    float *bmax = reinterpret_cast<float *>(wfl + nw);                     // [nw] >= every current distance of the block (>= 0)
+    float *s_blo = bmax + nw, *s_bhi = s_blo + nw;                         // [nw] norm range of the block
+    int *list = reinterpret_cast<int *>(s_bhi + nw);                       // [nw]
     unsigned *dirty = reinterpret_cast<unsigned *>(list + nw);             // [ceil(nw/32)]
-    unsigned char *wflag = reinterpret_cast<unsigned char *>(dirty + (nw + 31) / 32);   // [nw]
-    float *wout = reinterpret_cast<float *>(wflag + ((nw + 3) & ~3));      // [256] prefix values of the cached window
+    float *wout = reinterpret_cast<float *>((reinterpret_cast<unsigned long long>(dirty + (nw + 31) / 32) + 15ull) & ~15ull);   // [256], 16-byte aligned: one staged window / its prefix values
 
     const float *Xf = X + f.chunk_off * D, *Xsf = Xs + f.chunk_off * D, *pnsf = pns + f.chunk_off;
     const int *permf = perm + f.chunk_off;
     float *upsf = ups + f.chunk_off, *upf = up + f.chunk_off;
     int *sidf = sid + f.chunk_off;
     const long long wo = gsc_win_off(f);
-    const float *blof = blo + wo, *bhif = bhi + wo;
     int4 *wsumf = wsum + wo;
     float *cenf = cen + (long long)f.slot * Kmax * D;
     float *cnf = cnorm + (long long)f.slot * Kmax;
 
     for (int w = tid; w < (N + 31) / 32; w += T) chosen[w] = 0u;
-    for (int w = tid; w < nw; w += T) { wexp[w] = -1; bmax[w] = INFINITY; wflag[w] = GSC_SF_BAD; entry[w] = 0.0f; }
+    for (int w = tid; w < nw; w += T) {
+        wexp[w] = -1; wfl[w] = GSC_SF_BAD; bmax[w] = INFINITY; entry[w] = 0.0f;
+        s_blo[w] = blo[wo + w]; s_bhi[w] = bhi[wo + w];
+    }
     for (int w = tid; w < (nw + 31) / 32; w += T) dirty[w] = 0xffffffffu;   // every window is summarised after step 0
     if (tid == 0) { entry[nw] = 0.0f; s_obj = 0.0f; s_nlist = 0; s_ndirty = 0; }
     GscXor128b g = {123456789ull, 362436069ull, 521288629ull, 88675123ull};
@@ -403,12 +336,16 @@ __global__ void __launch_bounds__(GSC_SEED2_T) k_seed2(const GscFrame *__restric
                     const int half = count >> 1, idx = first + half, w = idx / GSC_SW;
                     bool gt;                    // target > r[idx]
                     const float lo = entry[w], hi = entry[w + 1];
-                    if (!(wflag[w] & (GSC_SF_NEG | GSC_SF_BAD)) && target > hi) gt = true;          // r[idx] <= exit sum < target
-                    else if (!(wflag[w] & (GSC_SF_NEG | GSC_SF_BAD)) && !(target > lo)) gt = false; // r[idx] >= entry sum >= target
+                    // monotone window: no element that can lower a sum of the entry's magnitude (flags made for an
+                    // exponent <= the entry's), nothing non-finite
+                    const int wf = wfl[w];
+                    const unsigned lob = __float_as_uint(lo);
+                    const bool mono = !(wf & (GSC_SF_NEG | GSC_SF_BAD)) && (lob >> 31) == 0u && (int)((lob >> 23) & 0xffu) >= (wf >> 8);
+                    if (mono && target > hi) gt = true;             // r[idx] <= exit sum < target
+                    else if (mono && !(target > lo)) gt = false;    // r[idx] >= entry sum >= target
                     else {
                         if (cached_w != w) {
-                            gsc_warp_chain(upf + w * GSC_SW, min(GSC_SW, N - w * GSC_SW), lo, wout);
-                            __syncwarp();
+                            gsc_warp_chain(upf + w * GSC_SW, min(GSC_SW, N - w * GSC_SW), lo, wout, true);
                             cached_w = w;
                         }
                         gt = target > wout[idx - w * GSC_SW];
@@ -422,14 +359,15 @@ __global__ void __launch_bounds__(GSC_SEED2_T) k_seed2(const GscFrame *__restric
                 if (c >= (unsigned)N) c = (unsigned)(N - 1);
                 chosen[c >> 5] |= 1u << (c & 31);
                 if (seeds) seeds[(long long)f.slot * Kmax + i] = (int)c;
-                float s = 0.0f;
+                float r[D];
+                gsc_load_row<D>(Xf, (long long)c, r);
+                float sn = 0.0f;
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    const float v = Xf[(long long)c * D + k];
-                    s_c[k] = v; cenf[(long long)i * D + k] = v;
-                    const float m = v * v; s = s + m;       // the norm load() cached for this point
+                    s_c[k] = r[k]; cenf[(long long)i * D + k] = r[k];
+                    const float m = r[k] * r[k]; sn = sn + m;       // the norm load() cached for this point
                 }
-                s_cn = s; cnf[i] = s;
+                s_cn = sn; cnf[i] = sn;
             }
             cached_w = -1;      // the distances change below
         }
@@ -461,7 +399,7 @@ __global__ void __launch_bounds__(GSC_SEED2_T) k_seed2(const GscFrame *__restric
                 const int b = b0 + tid;
                 bool take = false;
                 if (b < nw) {
-                    const float lo = blof[b], hi = bhif[b];
+                    const float lo = s_blo[b], hi = s_bhi[b];
                     const float gp = fmaxf(lo - scn, scn - hi);
                     // every point of the block has (sqrt(pn) - scn)^2 (1 - mrg) - mrg (cn + pn) - 1e-37 >= lbb
                     const float lbb = gp * gp * (1.0f - 2.0f * mrg) - mrg * (cn + hi * hi * 1.000001f) - 1e-37f;
@@ -477,33 +415,50 @@ __global__ void __launch_bounds__(GSC_SEED2_T) k_seed2(const GscFrame *__restric
             const int nl = s_nlist;
             if (tid == 0) n_blocks += nl;
             for (int li = warp; li < nl; li += W) {
-                const int b = list[li];
-                const int kend = min(N, (b + 1) * GSC_SW);
-                float mx = 0.0f;
-                // a point's row is only fetched when the new seed can lower its distance: d >= (|p| - |c|)^2, and
-                // yakmo's float evaluation of d stays within a few ulps of (cn + pn) of the true value; the margins
-                // cover both, so `up > d` is false for every skipped point
-#pragma unroll 2
-                for (int k = b * GSC_SW + lane; k < kend; k += 32) {
-                    const float pj = pnsf[k];
-                    float uj = upsf[k];
-                    const float t = sqrtf(pj) - scn;
-                    const float lb = t * t * (1.0f - mrg) - mrg * (cn + pj) - 1e-37f;
-                    if (!(lb > uj)) {
-                        float p[D];
-                        gsc_load_row<D>(Xsf, k, p);
-                        const float d = gsc_yakmo_dist<D>(p, pj, crow, cn);
-                        if (uj > d) {
-                            const int j = permf[k];
-                            upsf[k] = d; upf[j] = d; sidf[j] = i;
-                            atomicOr(&dirty[(j / GSC_SW) >> 5], 1u << ((j / GSC_SW) & 31));
-                            uj = d;
-                        }
-                    }
-                    mx = fmaxf(mx, uj);
+                const int kb = list[li] * GSC_SW;
+                const int kend = min(N, kb + GSC_SW);
+                // the norms and current distances of the lane's 8 points first (16 loads in flight), then the rows of
+                // the points the seed can still reach, two at a time.  A row is only fetched when the new seed can
+                // lower the distance: d >= (|p| - |c|)^2, and yakmo's float evaluation of d stays within a few ulps of
+                // (cn + pn) of the true value; the margins cover both, so `up > d` is false for every skipped point
+                float pj[8], uj[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = kb + q * 32 + lane;
+                    pj[q] = (k < kend) ? pnsf[k] : 0.0f;
+                    uj[q] = (k < kend) ? upsf[k] : -INFINITY;
                 }
+                unsigned pass = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float t = sqrtf(pj[q]) - scn;
+                    const float lb = t * t * (1.0f - mrg) - mrg * (cn + pj[q]) - 1e-37f;
+                    if (kb + q * 32 + lane < kend && !(lb > uj[q])) pass |= 1u << q;
+                }
+#pragma unroll
+                for (int h = 0; h < 8; h += 2) {
+                    float p[2][D];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if ((pass >> (h + q)) & 1u) gsc_load_row<D>(Xsf, kb + (h + q) * 32 + lane, p[q]);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if ((pass >> (h + q)) & 1u) {
+                            const int k = kb + (h + q) * 32 + lane;
+                            const float d = gsc_yakmo_dist<D>(p[q], pj[h + q], crow, cn);
+                            if (uj[h + q] > d) {
+                                const int j = permf[k];
+                                upsf[k] = d; upf[j] = d; sidf[j] = i;
+                                atomicOr(&dirty[(j / GSC_SW) >> 5], 1u << ((j / GSC_SW) & 31));
+                                uj[h + q] = d;
+                            }
+                        }
+                }
+                float mx = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) mx = fmaxf(mx, uj[q]);     // (-inf for the lanes past the end, NaN ignored)
                 mx = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(mx, 0.0f))));
-                if (lane == 0) bmax[b] = mx;
+                if (lane == 0) bmax[list[li]] = mx;
             }
         }
         __syncthreads();
@@ -529,42 +484,65 @@ __global__ void __launch_bounds__(GSC_SEED2_T) k_seed2(const GscFrame *__restric
                     int4 sm;
                     int fl;
                     gsc_window_summary(upf + w * GSC_SW, min(GSC_SW, N - w * GSC_SW), wexp[w], sm, fl);
-                    if (lane == 0) { wsumf[w] = sm; wflag[w] = (unsigned char)fl; }
+                    if (lane == 0) { wsumf[w] = sm; wfl[w] = fl; }
                 }
             }
             __syncthreads();
             if (tid == 0) { s_ndirty = 0; const unsigned long long t1 = clock64(); c_sum += t1 - c_t; c_t = t1; }   // (next use: next step)
             // ================= chain (warp 0): exact entry sum of every window, exact total =================
+            // 32 windows at a time, one per lane: the summaries that can apply in the running sum's binade are composed
+            // by a warp scan, every lane checks its own window against the entry sum the scan gives it, and the windows
+            // before the first one that fails are final.  That window is evaluated element by element (gsc_warp_chain);
+            // the scan resumes behind it.
             if (warp == 0) {
                 float run = 0.0f;
                 for (int wb = 0; wb < nw; wb += 32) {
-                    const int wl = wb + lane;
+                    const int wl = wb + lane, cntw = min(32, nw - wb);
                     int4 sm = make_int4(0, 0, 0, 0);
-                    int ep = -2, fl = GSC_SF_BAD;
-                    if (wl < nw) { sm = wsumf[wl]; ep = wexp[wl]; fl = wflag[wl]; }
+                    int ep = -2, fl = GSC_SF_BAD, fe = 0;
+                    if (wl < nw) { sm = wsumf[wl]; ep = wexp[wl]; const int wf = wfl[wl]; fl = wf & 3; fe = wf >> 8; }
                     float my_entry = 0.0f;
                     int my_newexp = ep;
-                    const int cntw = min(32, nw - wb);
-                    for (int l = 0; l < cntw; ++l) {
-                        const int f0 = __shfl_sync(FULL, sm.x, l), f1 = __shfl_sync(FULL, sm.y, l);
-                        const int ng = __shfl_sync(FULL, sm.z, l), ps = __shfl_sync(FULL, sm.w, l);
-                        const int epl = __shfl_sync(FULL, ep, l), fll = __shfl_sync(FULL, fl, l);
+                    int start = 0;
+                    while (start < cntw) {
                         const unsigned rb = __float_as_uint(run);
                         const int ea = (int)((rb >> 23) & 0xffu);
-                        const int S = (int)((rb & 0x7fffffu) | 0x800000u);
-                        if (lane == l) my_entry = run;
-                        const bool ok = !(fll & GSC_SF_BAD) && (rb >> 31) == 0u && ea == epl && ea >= 24 && ea <= 250 &&
-                                        S - ng >= (1 << 23) && S + ps < (1 << 24);
-                        if (ok) {
-                            const int Se = S + ((S & 1) ? f1 : f0);
-                            run = __uint_as_float(((unsigned)ea << 23) | ((unsigned)Se & 0x7fffffu));
-                        } else {
-                            const int w = wb + l;
-                            run = gsc_warp_chain(upf + w * GSC_SW, min(GSC_SW, N - w * GSC_SW), run, nullptr);
+                        const int S0 = (int)((rb & 0x7fffffu) | 0x800000u);
+                        const bool normal = (rb >> 31) == 0u && ea >= 26 && ea <= 250;
+                        int firstbad = start;
+                        if (normal) {
+                            const bool in = lane >= start && lane < cntw;
+                            const bool cand = in && !(fl & GSC_SF_BAD) && fe == ea;    // a summary made for this binade
+                            int s0 = cand ? sm.x : 0, s1 = cand ? sm.y : 0;            // (identity for the others)
+#pragma unroll
+                            for (int of = 1; of < 32; of <<= 1) {
+                                const int p0 = __shfl_up_sync(FULL, s0, of), p1 = __shfl_up_sync(FULL, s1, of);
+                                if (lane >= of) { int q0 = p0, q1 = p1; gsc_pf_compose(q0, q1, s0, s1); s0 = q0; s1 = q1; }
+                            }
+                            int x0 = __shfl_up_sync(FULL, s0, 1), x1 = __shfl_up_sync(FULL, s1, 1);
+                            if (lane == 0) { x0 = 0; x1 = 0; }
+                            const int Sen = S0 + ((S0 & 1) ? x1 : x0);      // entry of this lane's window if all before it hold
+                            const bool ok = !in || (cand && Sen - sm.z >= (1 << 23) && Sen + sm.w < (1 << 24));
+                            const unsigned badm = __ballot_sync(FULL, !ok);
+                            firstbad = badm ? (__ffs(badm) - 1) : cntw;
+                            if (in && lane < firstbad) my_entry = gsc_mkf(ea, Sen);
+                            const int e0 = __shfl_sync(FULL, s0, 31), e1 = __shfl_sync(FULL, s1, 31);
+                            const int Sfb = __shfl_sync(FULL, Sen, firstbad & 31);
+                            run = gsc_mkf(ea, (firstbad < cntw) ? Sfb : S0 + ((S0 & 1) ? e1 : e0));
+                        }
+                        if (firstbad < cntw) {
+                            const int w = wb + firstbad;
+                            const unsigned rb2 = __float_as_uint(run);
+                            const int ea2 = (int)((rb2 >> 23) & 0xffu);
+                            if (lane == firstbad) my_entry = run;
+                            run = gsc_warp_chain(upf + w * GSC_SW, min(GSC_SW, N - w * GSC_SW), run, wout, false);
                             if (lane == 0) ++n_exact;
-                            // the summary was made for another exponent (or none): make it for this one next step
-                            const int eu = ((rb >> 31) == 0u && ea >= 24 && ea <= 250) ? ea : -1;
-                            if (eu != epl && lane == l) my_newexp = eu;
+                            // a summary made for another exponent (or none): make it for this one at the next step
+                            const int eu = ((rb2 >> 31) == 0u && ea2 >= 26 && ea2 <= 250) ? ea2 : -1;
+                            if (lane == firstbad && eu != ep) my_newexp = eu;
+                            start = firstbad + 1;
+                        } else {
+                            start = cntw;
                         }
                     }
                     if (wl < nw) {
