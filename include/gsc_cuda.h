@@ -265,6 +265,7 @@ int gsc_fetch_quality(gsc_ctx *ctx, int n_frames, uint64_t *sq_err, int64_t *sam
 #define GSC_DBG_SEED_SERIAL   4u   /* ... and evaluates yakmo's float prefix sum with a one-warp serial chain */
 #define GSC_DBG_KNNFIT_DENSE  8u   /* KNNFit scans all entries twice instead of walking the norm window */
 #define GSC_DBG_LLOYD_OWNER   16u  /* Lloyd update by per-cluster owner threads (ordered sums) instead of the scatter */
+#define GSC_DBG_ONLINE_BATCHED 32u /* K <= 256: the batched CTA-per-frame kernel instead of the warp-per-frame one */
 int gsc_ctx_set_debug(gsc_ctx *ctx, unsigned flags);
 /* Debug: counters of the last online k-means launch, 16 x uint64 per frame:
  * batches, points, re-filtered points, resolver rounds, full candidate lists,

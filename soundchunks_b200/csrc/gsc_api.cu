@@ -121,7 +121,7 @@ struct gsc_ctx {
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
         use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke, sbytes, snb, sqerr,
-        perm, pns, xs, blo, bhi, wsum;
+        perm, pns, xs, blo, bhi, wsum, cstate, odone;
     unsigned debug = 0;              // GSC_DBG_* (gsc_ctx_set_debug): cross-check paths for the parity tests
     HostBuf hpcm, hout, hstream;
     const short *pcm_view = nullptr;   // PCM of the last batch on the device (own buffer or the caller's)
@@ -199,7 +199,7 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
                       &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr, &c->scompact, &c->soffs,
-                      &c->perm, &c->pns, &c->xs, &c->blo, &c->bhi, &c->wsum};
+                      &c->perm, &c->pns, &c->xs, &c->blo, &c->bhi, &c->wsum, &c->cstate, &c->odone};
     for (DevBuf *b : bufs) b->release();
     c->hsizes.release();
     c->hpcm.release();
@@ -483,14 +483,27 @@ static float online_slack() {
     return v;
 }
 
+// Passes per launch of k_online.  Frames need 10..100 passes and nobody knows which in advance; a launch that ran
+// every frame to its end would leave the SMs of the short frames idle behind the long ones.  In slices every
+// unfinished frame advances by the same few passes per launch, so the CTAs of a launch are equally long and the two
+// internal lanes' launches fill each other's last wave.  GSC_ONLINE_SLICE overrides (>= max_passes: one launch).
+static int online_slice() {
+    static const int v = [] { const char *e = getenv("GSC_ONLINE_SLICE"); const int x = e ? atoi(e) : 8; return x >= 1 ? x : 8; }();
+    return v;
+}
+
 template <int D, int CPT, int T>
 static int online_launch(gsc_ctx *c, double tol, int max_passes, int force_exact) {
     size_t smem = GscOnLayout<D, CPT, T>::TOTAL;
     auto k_online_inst = k_online<D, CPT, T>;
     SMEM_OPTIN(k_online_inst, smem);
-    LAUNCH(c, k_online_inst, c->F, T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
-           c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, force_exact,
-           online_slack(), c->dbg.as<unsigned long long>());
+    const int P = online_slice();
+    TRY(c->cstate.ensure(4 * (size_t)c->F * c->Kmax)); TRY(c->odone.ensure(4 * (size_t)c->F));
+    CU(cudaMemsetAsync(c->odone.p, 0, 4 * (size_t)c->F, c->stream));
+    for (int p0 = 0; p0 < max_passes; p0 += P)
+        LAUNCH(c, k_online_inst, c->F, T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
+               c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, force_exact,
+               online_slack(), c->dbg.as<unsigned long long>(), P, c->cstate.as<int>(), c->odone.as<int>());
     return GSC_OK;
 }
 
@@ -528,6 +541,17 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     const int K = c->Kmax, fe = (c->debug & GSC_DBG_ONLINE_EXACT) ? 1 : 0;
     // CTA shape by dictionary size: small K -> small CTAs so that several frames share an SM.  Only shapes that
     // compile without register spills are used (build.py checks).
+    // K <= 256: one warp per frame, the codebook in registers, the rule run literally (k_online_warp)
+    if (K <= 32 * GSC_OW_CPL && !(c->debug & GSC_DBG_ONLINE_BATCHED) && (D == 8 || D == 4)) {
+        const int grid = (c->F + GSC_OW_WARPS - 1) / GSC_OW_WARPS;
+        if (D == 8)
+            LAUNCH(c, k_online_warp<8>, grid, 32 * GSC_OW_WARPS, 0, c->frames.as<GscFrame>(), c->F, c->feat.as<float>(),
+                   c->cen.as<float>(), c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax);
+        else
+            LAUNCH(c, k_online_warp<4>, grid, 32 * GSC_OW_WARPS, 0, c->frames.as<GscFrame>(), c->F, c->feat.as<float>(),
+                   c->cen.as<float>(), c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax);
+        return GSC_OK;
+    }
     if (D == 8) {
         if (K <= 256) return online_launch<8, 4, 64>(c, tol, max_passes, fe);
         if (K <= 512) return online_launch<8, 4, 128>(c, tol, max_passes, fe);

@@ -256,7 +256,11 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                                               int *__restrict__ passes_out,      // [F]
                                               double *__restrict__ err_out,      // [F]
                                               double tol, int max_passes, int Kmax, int force_exact, float slack,
-                                              unsigned long long *__restrict__ dbg) {
+                                              unsigned long long *__restrict__ dbg,
+                                              // a launch runs at most `slice_passes` passes of every unfinished frame; the
+                                              // frame's state between launches is its centroids, labels, pass count,
+                                              // error sum and the hit counts of its last pass (original centroid order)
+                                              int slice_passes, int *__restrict__ cnt_state, int *__restrict__ done) {
     using Ly = GscOnLayout<D, CPT, T>;
     static_assert(T >= 64, "thread 32 accumulates the error sum");
     constexpr int DF = (D >= 8) ? D / 2 : D;   // filter dimensions
@@ -275,7 +279,11 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
     const GscFrame f = frames[blockIdx.x];
     const int K = f.K, N = f.N;
     if (K <= 0) return;
+    if (done[f.slot]) return;                 // stopped in an earlier slice
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *cst = cnt_state + (long long)f.slot * Kmax;
+    const int iter0 = passes_out[f.slot];     // passes completed by earlier slices
+    const int iter_end = min(max_passes, iter0 + slice_passes);
     // cell = CPT consecutive slots of the c0-sorted codebook.  Consecutive cells go to different warps (cell c ->
     // warp c % W, lane c / W): neighbouring points have neighbouring c0, so a batch hits a few neighbouring cells
     // and this spreads them over all warps.
@@ -302,7 +310,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
         for (int k = 0; k < D; ++k) r[k] = (i < K) ? cf[(long long)i * D + k] : __int_as_float(0x7fc00000);
         gsc_sts_row<D>(sb + Ly::C + (unsigned)i * D * 4, r);
         gsc_sts_u16(sb + Ly::S2O + 2u * i, i);
-        gsc_sts_i(sb + Ly::CNT + 4u * i, 1);  // enc:717-721
+        gsc_sts_i(sb + Ly::CNT + 4u * i, (iter0 > 0 && i < K) ? cst[i] : 1);  // enc:717-721 / the last pass's hits
     }
     for (int j = tid; j < N; j += T) {   // incoming guesses
         const int gg = lab[j];
@@ -315,13 +323,13 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
     gsc_sts_i(sb + Ly::DIRTY + 4u * tid, 0);
     if (tid < B) gsc_sts_i(sb + Ly::LISTN + 4u * tid, 0);
     if (tid == 0) {
-        gsc_sts_d(sb + Ly::ERR, 3.40282346638528860e+38);
+        gsc_sts_d(sb + Ly::ERR, iter0 > 0 ? err_out[f.slot] : 3.40282346638528860e+38);
         gsc_sts_i(sb + Ly::STOP, 0); gsc_sts_i(sb + Ly::MODE, GSC_MODE_DONE);
     }
     __syncthreads();
 
     unsigned long long c_batches = 0, c_exh = 0, c_rounds = 0, c_over = 0, c_points = 0, c_cands = 0;
-    int iter = 0;
+    int iter = iter0;
     for (;;) {
         // The reference keeps cnts[2][K]: a pass reads cnts[not Odd(iter)] (the previous pass's hits + 1) for the
         // rates, counts into cnts[Odd(iter)] and resets the array it read to 1.  The read array is only needed for
@@ -857,9 +865,9 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
             gsc_sts_i(sb + Ly::STOP, (same || iter >= max_passes) ? 1 : 0);
         }
         __syncthreads();
-        if (gsc_lds_i(sb + Ly::STOP)) break;
+        if (gsc_lds_i(sb + Ly::STOP) || iter >= iter_end) break;
     }
-    // the shared rows are the truth; back to the caller's order: centroid rows and labels by original index
+    // the shared rows are the truth; back to the caller's order: centroid rows, hit counts and labels by original index
     for (int j = 0; j < CPT; ++j) {
         const int idx = first + j;
         const int o = gsc_lds_u16(sb + Ly::S2O + 2u * idx);
@@ -868,6 +876,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
             gsc_lds_row<D>(sb + Ly::C + (unsigned)idx * D * 4, r);
 #pragma unroll
             for (int k = 0; k < D; ++k) cf[(long long)o * D + k] = r[k];
+            cst[o] = gsc_lds_i(sb + Ly::CNT + 4u * (unsigned)idx);
         }
     }
     for (int j = tid; j < N; j += T) {
@@ -877,9 +886,117 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
     if (tid == 0) {
         passes_out[f.slot] = iter;
         err_out[f.slot] = gsc_lds_d(sb + Ly::ERR);
+        done[f.slot] = gsc_lds_i(sb + Ly::STOP);
         if (dbg) {
             unsigned long long *o = dbg + (long long)f.slot * 16;
-            o[0] = c_batches; o[1] = c_points; o[2] = c_exh; o[3] = c_rounds; o[4] = c_over; o[5] = c_cands;
+            o[0] += c_batches; o[1] += c_points; o[2] += c_exh; o[3] += c_rounds; o[4] += c_over; o[5] += c_cands;
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Small dictionaries (K <= 256: the -cpf256 low-bitrate mode, BASELINE.json configs[2]): ONE WARP PER FRAME.
+// With 256 centroids the whole codebook fits the warp's registers (lane l owns centroids l, l+32, ... l+224: 8 rows
+// of D floats), so the reference's rule (enc:699-765) is run literally, one point after the other, with no
+// batching, speculation or block barrier: every lane scores the point against its 8 rows in the exact operation
+// order (ANN: sum (x-c)^2 left to right, no FMA), two redux steps give the nearest centroid with the lowest index on
+// ties, the owning lane moves its row.  The per-batch machinery of k_online (filter, lists, resolver rounds, three
+// block barriers per batch) costs more than scoring 256 centroids outright; here the warps of an SM are independent
+// frames and keep its issue slots busy.  Points are fetched 32 at a time (one row per lane) and broadcast by
+// shuffles; labels are written back coalesced per tile; lane 0 carries the Double error sum in point order.
+// grid = ceil(F / GSC_OW_WARPS), block = 32 * GSC_OW_WARPS.
+// ---------------------------------------------------------------------------
+#define GSC_OW_WARPS 2
+#define GSC_OW_CPL 8          // centroids per lane
+
+template <int D>
+__global__ void __maxnreg__(184) k_online_warp(const GscFrame *__restrict__ frames, int F,
+                                                                   const float *__restrict__ X,    // [sumN][D]
+                                                                   float *__restrict__ cen,        // [F][Kmax][D] in/out
+                                                                   int *__restrict__ labels,       // [sumN] out
+                                                                   int *__restrict__ passes_out,   // [F]
+                                                                   double *__restrict__ err_out,   // [F]
+                                                                   double tol, int max_passes, int Kmax) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int CPL = GSC_OW_CPL;
+    const int lane = threadIdx.x & 31;
+    const int fi = blockIdx.x * GSC_OW_WARPS + (threadIdx.x >> 5);
+    if (fi >= F) return;
+    const GscFrame f = frames[fi];
+    const int K = f.K, N = f.N;
+    if (K <= 0) return;
+    const float *Xf = X + f.chunk_off * D;
+    int *lab = labels + f.chunk_off;
+    float *cf = cen + (long long)f.slot * Kmax * D;
+
+    float c[CPL][D], rate[CPL];
+    int cnt[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int ci = lane + 32 * j;
+#pragma unroll
+        for (int k = 0; k < D; ++k) c[j][k] = (ci < K) ? cf[(long long)ci * D + k] : __int_as_float(0x7fc00000);   // dead rows never win
+        cnt[j] = 1;                                                                                                 // enc:717-721
+    }
+    double err = 3.40282346638528860e+38;   // enc:724 (all lanes carry the same value)
+    int iter = 0;
+    for (;;) {
+        const double prevErr = err;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) { rate[j] = gsc_rate(cnt[j]); cnt[j] = 1; }   // enc:735 (cnt_prev is constant during a pass), 754-758
+        double e_run = 0.0;
+        for (int base = 0; base < N; base += 32) {
+            const int tn = min(32, N - base);
+            float xt[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) xt[k] = 0.0f;
+            if (lane < tn) gsc_load_row<D>(Xf, base + lane, xt);
+            int mylab = 0;
+            for (int p = 0; p < tn; ++p) {
+                float x[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) x[k] = __shfl_sync(FULL, xt[k], p);
+                // nearest of this lane's rows: ascending j = ascending centroid index, strict < keeps the lowest
+                float bd = INFINITY;
+                int bj = -1;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const float d = gsc_ann_dist<D>(x, c[j]);
+                    if (d < bd) { bd = d; bj = j; }
+                }
+                const unsigned dk = (bj >= 0) ? __float_as_uint(bd) : 0xffffffffu;      // distances are >= 0: bits order them
+                const unsigned m = __reduce_min_sync(FULL, dk);
+                const unsigned ci = __reduce_min_sync(FULL, (dk == m && bj >= 0) ? (unsigned)(lane + 32 * bj) : 0xffffffffu);
+                int win = (int)ci;
+                float dw = __uint_as_float(m);
+                if (ci == 0xffffffffu) { win = 0; dw = INFINITY; }                       // every row NaN: centroid 0, d = +inf
+                if (lane == (win & 31)) {
+                    // enc:735-740, 744 on the winning row (static register indices: one case per owned row)
+                    switch (win >> 5) {
+#define GSC_OW_CASE(J) case J: { _Pragma("unroll") for (int k = 0; k < D; ++k) { const float v = x[k] - c[J][k]; const float mm = v * rate[J]; c[J][k] = c[J][k] + mm; } cnt[J] += 1; } break;
+                        GSC_OW_CASE(0) GSC_OW_CASE(1) GSC_OW_CASE(2) GSC_OW_CASE(3)
+                        GSC_OW_CASE(4) GSC_OW_CASE(5) GSC_OW_CASE(6) GSC_OW_CASE(7)
+#undef GSC_OW_CASE
+                        default: break;
+                    }
+                }
+                if (lane == p) mylab = win;                                             // enc:742
+                e_run += (double)sqrtf(dw / (float)D);                                  // enc:743 (same value in every lane)
+            }
+            if (lane < tn) lab[base + lane] = mylab;
+        }
+        err = e_run;
+        ++iter;
+        const bool same = (err > prevErr) ? ((err - prevErr) <= tol) : ((prevErr - err) <= tol);   // enc:761
+        if (same || iter >= max_passes) break;
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int ci = lane + 32 * j;
+        if (ci < K) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) cf[(long long)ci * D + k] = c[j][k];
+        }
+    }
+    if (lane == 0) { passes_out[f.slot] = iter; err_out[f.slot] = err; }
 }
