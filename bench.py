@@ -458,6 +458,15 @@ def main():
                                "scaling": "strong", "frames_per_rank": len(mine), "value": 3600.0 / (ms * 1e-3), "unit": UNIT,
                                "ms_per_step": ms}
         del d48, h48
+        # -- split_frame: BASELINE.json configs[3], the only collective of the encoder (inside the library, NCCL)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from split_frame import run_split
+
+        def bcast(b):
+            obj = [b]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+        extras["split_frame"] = run_split(ctx, rank, world, 1 << 20, 4096, 10, bcast, max_over_ranks)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

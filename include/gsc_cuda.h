@@ -61,10 +61,12 @@ void yakmo_train_on_data(void *ay, int32_t *pointToCluster);
 /* ext:116  writes k rows of colCount floats into caller-owned rows. */
 void yakmo_get_centroids(void *ay, float **centroids);
 
-/* ext:118  pa = n row pointers of dd floats.  The points are SNAPSHOT to the
- *          device at create time (ANN aliases the caller's rows instead; see
- *          INTEGRATION.md for what that changes in enc:699-765).  bs and
- *          split are kd-tree hints and are ignored by the exact GPU search. */
+/* ext:118  pa = n row pointers of dd floats.  Like ANN, the handle KEEPS the
+ *          caller's row pointers (they must stay valid until destroy): before
+ *          every query the rows are re-read and whatever changed is uploaded, so
+ *          the enc:725-746 loop, which moves Centroids[bestIdx] between queries
+ *          on one tree, sees its own updates.  bs and split are kd-tree hints
+ *          and are ignored by the exact GPU search (no stale planes either). */
 void *ann_kdtree_create(float **pa, int32_t n, int32_t dd, int32_t bs,
                         int32_t split);
 /* ext:119  destroy(NULL) is a no-op. */
@@ -165,6 +167,23 @@ int gsc_split_step(gsc_ctx *ctx, double *acc_dev);
 int gsc_split_update(gsc_ctx *ctx, const double *acc_dev);
 /* final assignment against the last centroids; both outputs optional */
 int gsc_split_end(gsc_ctx *ctx, float *centroids, int32_t *labels);
+
+/* The same split with the collective INSIDE the library: NCCL (bound at run time from libnccl.so.2) over
+ * NVLink / NVSwitch, one context per rank.  Rank 0 makes an id (gsc_split_unique_id) and hands the 128 bytes to
+ * the other ranks by whatever transport the host has; every rank calls gsc_split_comm_init.  gsc_split_seed gives
+ * all ranks the same start (yakmo's k-means++ on rank 0's shard, broadcast); gsc_split_lloyd runs
+ * `iters` x (assign, Double partial sums, ncclAllReduce(sum) of K x (D+1) doubles, means) + a final assignment on
+ * the context's stream without a host synchronisation inside the loop.  centroids: in = the start (identical on
+ * every rank), out = the result (identical on every rank, and bit-identical to gsc_lloyd on the whole frame:
+ * Double accumulation, one rounding to Single).  ms_out (optional): 3 doubles from CUDA events -- the loop, the
+ * time inside the all-reduces, the first iteration.  Without gsc_split_comm_init the call runs on one rank. */
+#define GSC_SPLIT_ID_BYTES 128
+int gsc_split_unique_id(char *id /* [GSC_SPLIT_ID_BYTES] */);
+int gsc_split_comm_init(gsc_ctx *ctx, int nranks, int rank, const char *id);
+int gsc_split_comm_destroy(gsc_ctx *ctx);
+int gsc_split_seed(gsc_ctx *ctx, const float *X_shard, int N, int D, int K, float *centroids);
+int gsc_split_lloyd(gsc_ctx *ctx, const float *X_shard, int N, int D, float *centroids, int K, int iters,
+                    int32_t *labels, double *ms_out);
 
 /* Exact nearest centroid per row (ANN-style distance). dist optional. */
 int gsc_assign(gsc_ctx *ctx, const float *X, int N, int D,

@@ -25,7 +25,8 @@ EXPORTS = [
     "gsc_last_error", "gsc_device_count", "gsc_create", "gsc_destroy", "gsc_ctx_device", "gsc_ctx_stream",
     "gsc_synchronize", "gsc_get_stats", "gsc_stage_busy_ms", "gsc_reset_stats",
     "gsc_find_attenuation_divider", "gsc_make_chunks", "gsc_yakmo", "gsc_knn_scan_reduce", "gsc_lloyd",
-    "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
+    "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end",
+    "gsc_split_unique_id", "gsc_split_comm_init", "gsc_split_comm_destroy", "gsc_split_seed", "gsc_split_lloyd", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
     "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_ctx_set_debug", "gsc_debug_online_counters", "gsc_debug_seed_counters",
 ]
@@ -293,6 +294,37 @@ class Context:
         self._ck(self.L.gsc_split_end(C.c_void_p(self.h), _vp(cen), _vp(labels)))
         return cen, labels
 
+    # ---- the same with NCCL inside the library (gsc_split_lloyd) ------------
+    @staticmethod
+    def split_unique_id() -> bytes:
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        if L.gsc_split_unique_id(buf) != 0:
+            raise GscError(L.gsc_last_error().decode())
+        return buf.raw
+
+    def split_comm_init(self, nranks: int, rank: int, uid: bytes):
+        self._ck(self.L.gsc_split_comm_init(C.c_void_p(self.h), nranks, rank, C.c_char_p(uid)))
+
+    def split_comm_destroy(self):
+        self._ck(self.L.gsc_split_comm_destroy(C.c_void_p(self.h)))
+
+    def split_seed(self, X_shard, K):
+        X = np.ascontiguousarray(X_shard, dtype=np.float32)
+        cen = np.zeros((K, X.shape[1]), np.float32)
+        self._ck(self.L.gsc_split_seed(C.c_void_p(self.h), _vp(X), X.shape[0], X.shape[1], K, _vp(cen)))
+        return cen
+
+    def split_lloyd(self, X_shard, centroids, iters):
+        """-> (centroids, labels of the shard, dict(ms_loop, ms_allreduce, ms_first_iter))"""
+        X = np.ascontiguousarray(X_shard, dtype=np.float32)
+        cen = np.array(centroids, dtype=np.float32, order="C", copy=True)
+        labels = np.zeros(X.shape[0], np.int32)
+        ms = (C.c_double * 3)()
+        self._ck(self.L.gsc_split_lloyd(C.c_void_p(self.h), _vp(X), X.shape[0], X.shape[1], _vp(cen), cen.shape[0], iters,
+                                        _vp(labels), ms))
+        return cen, labels, dict(ms_loop=ms[0], ms_allreduce=ms[1], ms_first_iter=ms[2])
+
     def assign(self, X, centroids):
         X = np.ascontiguousarray(X, dtype=np.float32)
         cen = np.ascontiguousarray(centroids, dtype=np.float32)
@@ -464,11 +496,15 @@ def legacy_yakmo(X: np.ndarray, k: int, max_iter: int = 0, init_type: int = 1):
 class LegacyAnn:
     """ann_kdtree_* as ext:118-123 binds them."""
 
-    def __init__(self, pts: np.ndarray):
+    def __init__(self, pts: np.ndarray, copy: bool = True):
+        """copy=False: the handle aliases the rows of `pts` itself (a C-contiguous float32 array the caller goes on
+        mutating, as enc:736-740 does); the row-pointer table is kept alive with the handle."""
         self.L = load_library()
-        self.pts = np.ascontiguousarray(pts, dtype=np.float32)
+        self.pts = np.ascontiguousarray(pts, dtype=np.float32) if copy else pts
+        assert self.pts.dtype == np.float32 and self.pts.flags.c_contiguous
         n, dd = self.pts.shape
-        self.h = self.L.ann_kdtree_create(_row_ptrs(self.pts), n, dd, 1, 0)
+        self._rows = _row_ptrs(self.pts)
+        self.h = self.L.ann_kdtree_create(self._rows, n, dd, 1, 0)
         if not self.h:
             raise GscError(self.L.gsc_last_error().decode())
 

@@ -5,6 +5,8 @@
 #include "../../include/gsc_cuda.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>          // types only: the library is bound at run time (dlopen), see gsc_split_*
 #include <xmmintrin.h>
 
 #include <atomic>
@@ -122,6 +124,8 @@ struct gsc_ctx {
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
         use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke, sbytes, snb, sqerr,
         perm, pns, xs, blo, bhi, wsum, cstate, odone;
+    void *nccl_comm = nullptr;       // ncclComm_t of the oversized-frame split (gsc_split_comm_init)
+    int nccl_ranks = 1, nccl_rank = 0;
     unsigned debug = 0;              // GSC_DBG_* (gsc_ctx_set_debug): cross-check paths for the parity tests
     HostBuf hpcm, hout, hstream;
     const short *pcm_view = nullptr;   // PCM of the last batch on the device (own buffer or the caller's)
@@ -193,6 +197,7 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
     FpGuard g;
     if (c->peer) { gsc_destroy(c->peer); c->peer = nullptr; }
     cudaSetDevice(c->device);
+    if (c->nccl_comm) gsc_split_comm_destroy(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->frames, &c->pcm, &c->divider, &c->vout, &c->attr, &c->atten, &c->feat, &c->dst,
                       &c->pnorm, &c->up, &c->r, &c->sid, &c->seeds, &c->cen, &c->cnorm, &c->sums, &c->cnt0,
@@ -412,12 +417,20 @@ static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
     TRY(c->blo.ensure(4 * nwin)); TRY(c->bhi.ensure(4 * nwin)); TRY(c->wsum.ensure(16 * nwin));
     LAUNCH(c, k_seed_prep<D>, c->F, 512, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->pnorm.as<float>(),
            c->perm.as<int>(), c->pns.as<float>(), c->xs.as<float>(), c->blo.as<float>(), c->bhi.as<float>());
-    SMEM_OPTIN(k_seed2<D>, smem);
-    LAUNCH(c, k_seed2<D>, c->F, GSC_SEED2_T, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->xs.as<float>(),
-           c->pns.as<float>(), c->perm.as<int>(), c->blo.as<float>(), c->bhi.as<float>(), init_type,
-           c->r.as<float>(), c->up.as<float>(), c->sid.as<int>(), c->wsum.as<int4>(),
-           want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax,
-           c->sdbg.as<unsigned long long>());
+    static const int seed_t = [] { const char *e = getenv("GSC_SEED_T"); const int x = e ? atoi(e) : 128; return (x == 64 || x == 256) ? x : 128; }();
+#define GSC_SEED2_LAUNCH(TT)                                                                                              \
+    do {                                                                                                                  \
+        SMEM_OPTIN((k_seed2<D, TT>), smem);                                                                               \
+        LAUNCH(c, (k_seed2<D, TT>), c->F, TT, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->xs.as<float>(),     \
+               c->pns.as<float>(), c->perm.as<int>(), c->blo.as<float>(), c->bhi.as<float>(), init_type,                  \
+               c->r.as<float>(), c->up.as<float>(), c->sid.as<int>(), c->wsum.as<int4>(),                                 \
+               want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax,              \
+               c->sdbg.as<unsigned long long>());                                                                         \
+    } while (0)
+    if (seed_t == 64) GSC_SEED2_LAUNCH(64);
+    else if (seed_t == 256) GSC_SEED2_LAUNCH(256);
+    else GSC_SEED2_LAUNCH(128);
+#undef GSC_SEED2_LAUNCH
     return GSC_OK;
 }
 
@@ -851,6 +864,144 @@ extern "C" int gsc_split_end(gsc_ctx *c, float *centroids, int32_t *labels) {
     if (centroids) TRY(d2h(c, centroids, c->cen.p, 4 * (size_t)K * D));
     if (labels) TRY(d2h(c, labels, c->labels.p, 4 * (size_t)c->sumN));
     return sync(c);
+}
+
+// ---- the same split with the collective inside the library (NCCL over NVLink / NVSwitch) ---------------------
+// libnccl is bound at run time: a host that never splits a frame does not need it, and inside a process that
+// already loaded a libnccl (PyTorch) the same copy is used.
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi &nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.h) break;
+        }
+        if (!a.h) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.h, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.h, "ncclCommDestroy");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(a.h, "ncclAllReduce");
+        a.Broadcast = (decltype(a.Broadcast))dlsym(a.h, "ncclBroadcast");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Broadcast && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+#define NC(call)                                                                                           \
+    do {                                                                                                   \
+        ncclResult_t r_ = (call);                                                                          \
+        if (r_ != ncclSuccess) return set_err(GSC_ERR_CUDA, "%s failed: %s", #call, nccl_api().GetErrorString(r_)); \
+    } while (0)
+
+static_assert(sizeof(ncclUniqueId) == GSC_SPLIT_ID_BYTES, "gsc_split_unique_id size");
+
+extern "C" int gsc_split_unique_id(char *id) {
+    FpGuard g;
+    if (!id) return set_err(GSC_ERR_ARG, "null argument");
+    if (!nccl_api().ok) return set_err(GSC_ERR_UNSUPPORTED, "libnccl.so.2 not found (needed only for the oversized-frame split)");
+    ncclUniqueId u;
+    NC(nccl_api().GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return GSC_OK;
+}
+extern "C" int gsc_split_comm_init(gsc_ctx *c, int nranks, int rank, const char *id) {
+    FpGuard g;
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return set_err(GSC_ERR_ARG, "bad arguments to gsc_split_comm_init");
+    if (!nccl_api().ok) return set_err(GSC_ERR_UNSUPPORTED, "libnccl.so.2 not found (needed only for the oversized-frame split)");
+    CU(cudaSetDevice(c->device));
+    if (c->nccl_comm) { nccl_api().CommDestroy((ncclComm_t)c->nccl_comm); c->nccl_comm = nullptr; }
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t comm;
+    NC(nccl_api().CommInitRank(&comm, nranks, u, rank));
+    c->nccl_comm = comm; c->nccl_ranks = nranks; c->nccl_rank = rank;
+    return GSC_OK;
+}
+extern "C" int gsc_split_comm_destroy(gsc_ctx *c) {
+    if (!c) return set_err(GSC_ERR_ARG, "null context");
+    if (c->nccl_comm) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        nccl_api().CommDestroy((ncclComm_t)c->nccl_comm);
+        c->nccl_comm = nullptr; c->nccl_ranks = 1; c->nccl_rank = 0;
+    }
+    return GSC_OK;
+}
+
+// Start centroids for the split: yakmo's k-means++ (k_seed2, exact) on rank 0's shard, its seed rows broadcast to
+// every rank.  (The reference seeds over the whole frame; a frame that does not fit one GPU has no single place
+// where that prefix sum could run, so the split's start is the seeding of the first shard -- a documented
+// substitution; the Lloyd iterations that follow are exact over all points.)
+extern "C" int gsc_split_seed(gsc_ctx *c, const float *X, int N, int D, int K, float *centroids) {
+    FpGuard g;
+    if (!c || !centroids) return set_err(GSC_ERR_ARG, "null argument");
+    if (K > N) return set_err(GSC_ERR_ARG, "k (%d) > rows of the shard (%d)", K, N);
+    TRY(upload_points(c, X, N, D, K));
+    TRY(c->cen.ensure(4 * (size_t)K * D));
+    if (c->nccl_rank == 0) {
+        TRY(c->labels.ensure(4 * (size_t)N));
+        const size_t n = (size_t)N, fk = (size_t)K;
+        TRY(c->pnorm.ensure(4 * n)); TRY(c->up.ensure(4 * n)); TRY(c->r.ensure(4 * n)); TRY(c->sid.ensure(4 * n));
+        TRY(c->cnorm.ensure(4 * fk));
+        DISPATCH_D(D, TRY(seed_launch<D>(c, 1, false)));      // cen := the K seed rows
+    }
+    if (c->nccl_comm && c->nccl_ranks > 1)
+        NC(nccl_api().Broadcast(c->cen.p, c->cen.p, (size_t)K * D, ncclFloat, 0, (ncclComm_t)c->nccl_comm, c->stream));
+    TRY(d2h(c, centroids, c->cen.p, 4 * (size_t)K * D));
+    return sync(c);
+}
+
+// `iters` x (exact assignment of the shard, Double partial sums, all-reduce of K x (D+1) doubles, means), then a
+// final assignment -- everything queued on the context's stream, no host synchronisation inside the loop.
+// ms_out (optional, 3 doubles, CUDA events): whole loop, time inside the all-reduces, first iteration.
+extern "C" int gsc_split_lloyd(gsc_ctx *c, const float *X, int N, int D, float *centroids, int K, int iters,
+                               int32_t *labels, double *ms_out) {
+    FpGuard g;
+    if (!c || !centroids || iters < 0) return set_err(GSC_ERR_ARG, "bad arguments to gsc_split_lloyd");
+    const bool multi = c->nccl_comm && c->nccl_ranks > 1;
+    TRY(upload_points(c, X, N, D, K));
+    TRY(c->cen.ensure(4 * (size_t)K * D));
+    TRY(h2d(c, c->cen.p, centroids, 4 * (size_t)K * D));
+    TRY(c->sums.ensure(8 * (size_t)K * (D + 1)));
+    TRY(c->labels.ensure(4 * (size_t)N));
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters + 2);
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    TRY(sync(c));                                            // uploads are not part of the timed loop
+    CU(cudaEventRecord(ev[2 * (size_t)iters], c->stream));
+    for (int it = 0; it < iters; ++it) {
+        TRY(stage_assign(c, D, false));
+        TRY(stage_lloyd_sums(c, D, c->sums.as<double>()));
+        CU(cudaEventRecord(ev[2 * (size_t)it], c->stream));
+        if (multi)
+            NC(nccl_api().AllReduce(c->sums.p, c->sums.p, (size_t)K * (D + 1), ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+        CU(cudaEventRecord(ev[2 * (size_t)it + 1], c->stream));
+        TRY(stage_lloyd_means(c, D, c->sums.as<double>()));
+    }
+    TRY(stage_assign(c, D, false));
+    CU(cudaEventRecord(ev[2 * (size_t)iters + 1], c->stream));
+    TRY(d2h(c, centroids, c->cen.p, 4 * (size_t)K * D));
+    if (labels) TRY(d2h(c, labels, c->labels.p, 4 * (size_t)N));
+    TRY(sync(c));
+    if (ms_out) {
+        float ms = 0, ar = 0, first = 0;
+        cudaEventElapsedTime(&ms, ev[2 * (size_t)iters], ev[2 * (size_t)iters + 1]);
+        for (int it = 0; it < iters; ++it) { float t = 0; cudaEventElapsedTime(&t, ev[2 * (size_t)it], ev[2 * (size_t)it + 1]); ar += t; }
+        if (iters > 0) cudaEventElapsedTime(&first, ev[2 * (size_t)iters], ev[1]);
+        ms_out[0] = ms; ms_out[1] = ar; ms_out[2] = first;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return GSC_OK;
 }
 
 extern "C" int gsc_build_dictionary(gsc_ctx *c, const int32_t *labels, const int16_t *pcm, int64_t stride, int C, int S,
@@ -1404,6 +1555,11 @@ struct AnnHandle {
     gsc_ctx *ctx = nullptr;
     int n = 0, dd = 0;
     DevBuf pts, q, scratch, idx, err;
+    // ANN keeps the caller's row pointers and reads the rows at query time; enc:736-740 moves a row
+    // between two queries on the same tree.  The handle keeps the pointers too, and before every query re-reads the
+    // rows: whatever changed since the last look is uploaded (one row per query in KNNScanReduce).
+    float **rows = nullptr;
+    std::vector<float> shadow;
 };
 
 extern "C" void *ann_kdtree_create(float **pa, int32_t n, int32_t dd, int32_t bs, int32_t split) {
@@ -1414,8 +1570,9 @@ extern "C" void *ann_kdtree_create(float **pa, int32_t n, int32_t dd, int32_t bs
     if (!ctx) return nullptr;
     AnnHandle *h = new (std::nothrow) AnnHandle();
     if (!h) { gsc_destroy(ctx); return nullptr; }
-    h->ctx = ctx; h->n = n; h->dd = dd;
-    std::vector<float> flat((size_t)n * dd);
+    h->ctx = ctx; h->n = n; h->dd = dd; h->rows = pa;
+    std::vector<float> &flat = h->shadow;
+    flat.resize((size_t)n * dd);
     for (int i = 0; i < n; ++i) memcpy(&flat[(size_t)i * dd], pa[i], sizeof(float) * dd);
     bool ok = h->pts.ensure(4 * (size_t)n * dd) == GSC_OK && h->q.ensure(4 * (size_t)dd) == GSC_OK &&
               h->scratch.ensure(4 * (size_t)n) == GSC_OK && h->idx.ensure(4 * 1024) == GSC_OK &&
@@ -1445,6 +1602,13 @@ static int ann_query(AnnHandle *h, const float *q, float eps, int cnt, int32_t *
     if (cnt > h->n) return set_err(GSC_ERR_ARG, "ann search: k > n");  // ANN: "Requesting more near neighbors than data points"
     gsc_ctx *c = h->ctx;
     CU(cudaSetDevice(c->device));
+    for (int i = 0; i < h->n; ++i) {                       // live rows: upload what the caller changed
+        float *sh = &h->shadow[(size_t)i * h->dd];
+        if (memcmp(sh, h->rows[i], sizeof(float) * h->dd) != 0) {
+            memcpy(sh, h->rows[i], sizeof(float) * h->dd);
+            TRY(h2d(c, h->pts.as<float>() + (size_t)i * h->dd, sh, sizeof(float) * h->dd));
+        }
+    }
     TRY(h2d(c, h->q.p, q, 4 * (size_t)h->dd));
     LAUNCH(c, k_ann_query, 1, 256, 0, h->pts.as<float>(), h->n, h->dd, h->q.as<float>(), cnt, h->scratch.as<float>(),
            h->idx.as<int>(), h->err.as<float>());

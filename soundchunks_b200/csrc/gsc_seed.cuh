@@ -32,7 +32,6 @@
 #include "gsc_device.cuh"
 
 #define GSC_SW 256            // elements per prefix-sum window = points per norm block
-#define GSC_SEED2_T 256       // threads per CTA of k_seed2
 #define GSC_SF_BAD 1          // window flags: an element that no binade summary can hold (non-finite)
 #define GSC_SF_NEG 2          //               a negative element (prefix sums not monotone inside the window)
 
@@ -261,8 +260,10 @@ __host__ __device__ inline size_t gsc_seed2_smem(int N) {
 
 __device__ __forceinline__ float gsc_mkf(int e, int S) { return __uint_as_float(((unsigned)e << 23) | ((unsigned)S & 0x7fffffu)); }
 
-template <int D>
-__global__ void __launch_bounds__(GSC_SEED2_T, 2) k_seed2(const GscFrame *__restrict__ frames,
+// T threads per CTA: every phase of a step is a latency chain (global loads, warp scans, a 256-long FADD chain), so
+// what keeps an SM busy is the number of independent frames resident on it, not the width of one CTA.
+template <int D, int T>
+__global__ void __launch_bounds__(T, 512 / T) k_seed2(const GscFrame *__restrict__ frames,
                                                           const float *__restrict__ X,     // [sumN][D] original order
                                                           const float *__restrict__ Xs,    // [sumN][D] bucketed order
                                                           const float *__restrict__ pns,   // [sumN] norms, bucketed order
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(GSC_SEED2_T, 2) k_seed2(const GscFrame *__rest
                                                           float *__restrict__ cnorm,       // [F][Kmax]
                                                           int Kmax, unsigned long long *__restrict__ sdbg) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int T = GSC_SEED2_T, W = T / 32;
+    constexpr int W = T / 32;
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ float s_c[D];
     __shared__ float s_cn, s_obj;

@@ -346,3 +346,56 @@ def test_device_stream_packer_and_quality(ctx, oracle, nframes, ch, bits):
                                                                          r.index, r.attr, r.overfull), ch, f.shape[1], 4, bits).ravel()
                              for f, r in zip(frames, res)])
     assert np.sqrt(tot / float(ns.sum())) == oracle.psy_a_delta(allsrc, allrec)
+
+
+def test_split_lloyd_in_library_matches_oracle(ctx, oracle):
+    """gsc_split_seed + gsc_split_lloyd (the oversized-frame entry points, NCCL communicator of one rank): the start
+    is yakmo's seed sequence on the shard, the result is oracle.lloyd's within BASELINE.json's 1e-4 relative (and
+    bit-identical to gsc_lloyd: Double accumulation, one rounding)."""
+    import soundchunks_b200 as sc
+    pcm, raw, attr, feat = _features(oracle, 1.5, ch=2, seed=5, sr=48000)
+    K, iters = 512, 4
+    uid = sc.Context.split_unique_id()
+    ctx.split_comm_init(1, 0, uid)
+    try:
+        c0 = ctx.split_seed(feat, K)
+        _, _, seeds = oracle.yakmo(feat, K)
+        assert np.array_equal(c0.view(np.uint32), feat[seeds].view(np.uint32))
+        cen, labels, ms = ctx.split_lloyd(feat, c0, iters)
+    finally:
+        ctx.split_comm_destroy()
+    ref_cen, ref_lab = oracle.lloyd(feat, c0, iters)
+    rel = np.max(np.abs(cen - ref_cen), axis=1) / np.maximum(np.max(np.abs(ref_cen), axis=1), 1e-12)
+    assert rel.max() <= 1e-4 and np.mean(labels != ref_lab) < 1e-4
+    g_cen, g_lab = ctx.lloyd(feat, c0, iters)
+    assert np.array_equal(cen.view(np.uint32), g_cen.view(np.uint32)) and np.array_equal(labels, g_lab)
+    assert ms["ms_loop"] > 0
+
+
+def test_legacy_ann_sees_the_callers_live_rows(ctx, oracle):
+    """ANN keeps the caller's row pointers: enc:725-746 moves Centroids[bestIdx] between queries on one
+    tree and later queries must see the moved row.  Driving that loop through the legacy ABI must give what
+    gsc_knn_scan_reduce gives."""
+    import soundchunks_b200 as sc
+    pcm, raw, attr, feat = _features(oracle, 0.06)
+    feat = np.ascontiguousarray(feat[:600])
+    K, D = 48, feat.shape[1]
+    c0, _, _ = oracle.yakmo(feat, K)
+    want = ctx.knn_scan_reduce(feat, c0, 3, 2)
+    cen = np.array(c0, np.float32, copy=True)
+    cnts = [np.ones(K, np.int32), np.ones(K, np.int32)]
+    labels = np.zeros(len(feat), np.int32)
+    for it in range(2):                                   # enc:725-761
+        kdt = sc.LegacyAnn(cen, copy=False)               # rows of `cen` itself, mutated below
+        err = 0.0
+        for i in range(len(feat)):
+            b, d2 = kdt.search(feat[i])
+            rate = np.float32(1.0 / np.sqrt(float(cnts[1 - (it & 1)][b])))
+            cen[b] = cen[b] + (feat[i] - cen[b]) * rate   # float32, operation by operation as enc:736-740
+            labels[i] = b
+            err += float(np.sqrt(np.float32(d2) / np.float32(D)))
+            cnts[it & 1][b] += 1
+        cnts[1 - (it & 1)][:] = 1
+        kdt.close()
+    assert np.array_equal(labels, want[1]) and np.array_equal(cen.view(np.uint32), want[0].view(np.uint32))
+    assert err == want[3]
