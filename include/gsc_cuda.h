@@ -171,7 +171,7 @@ int gsc_split_end(gsc_ctx *ctx, float *centroids, int32_t *labels);
 /* The same split with the collective INSIDE the library: NCCL (bound at run time from libnccl.so.2) over
  * NVLink / NVSwitch, one context per rank.  Rank 0 makes an id (gsc_split_unique_id) and hands the 128 bytes to
  * the other ranks by whatever transport the host has; every rank calls gsc_split_comm_init.  gsc_split_seed gives
- * all ranks the same start (yakmo's k-means++ on rank 0's shard, broadcast); gsc_split_lloyd runs
+ * all ranks the same start (yakmo's k-means++ on the first <= 524,288 rows of rank 0's shard, broadcast); gsc_split_lloyd runs
  * `iters` x (assign, Double partial sums, ncclAllReduce(sum) of K x (D+1) doubles, means) + a final assignment on
  * the context's stream without a host synchronisation inside the loop.  centroids: in = the start (identical on
  * every rank), out = the result (identical on every rank, and bit-identical to gsc_lloyd on the whole frame:
@@ -285,6 +285,7 @@ int gsc_fetch_quality(gsc_ctx *ctx, int n_frames, uint64_t *sq_err, int64_t *sam
 #define GSC_DBG_KNNFIT_DENSE  8u   /* KNNFit scans all entries twice instead of walking the norm window */
 #define GSC_DBG_LLOYD_OWNER   16u  /* Lloyd update by per-cluster owner threads (ordered sums) instead of the scatter */
 #define GSC_DBG_ONLINE_BATCHED 32u /* K <= 256: the batched CTA-per-frame kernel instead of the warp-per-frame one */
+#define GSC_DBG_LABEL_SCAN     64u /* per-cluster sums by scanning all labels per cluster (O(K*N)) instead of member lists */
 int gsc_ctx_set_debug(gsc_ctx *ctx, unsigned flags);
 /* Debug: counters of the last online k-means launch, 16 x uint64 per frame:
  * batches, points, re-filtered points, resolver rounds, full candidate lists,

@@ -200,7 +200,7 @@ class Context:
         self._ck(self.L.gsc_debug_online_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
 
-    DBG_ONLINE_EXACT, DBG_SEED_FULLSCAN, DBG_SEED_SERIAL, DBG_KNNFIT_DENSE, DBG_LLOYD_OWNER, DBG_ONLINE_BATCHED = 1, 2, 4, 8, 16, 32
+    DBG_ONLINE_EXACT, DBG_SEED_FULLSCAN, DBG_SEED_SERIAL, DBG_KNNFIT_DENSE, DBG_LLOYD_OWNER, DBG_ONLINE_BATCHED, DBG_LABEL_SCAN = 1, 2, 4, 8, 16, 32, 64
 
     def set_debug(self, flags: int):
         """Cross-check paths (include/gsc_cuda.h GSC_DBG_*); 0 = the product path."""

@@ -123,7 +123,7 @@ struct gsc_ctx {
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
         use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke, sbytes, snb, sqerr,
-        perm, pns, xs, blo, bhi, wsum, cstate, odone;
+        perm, pns, xs, blo, bhi, wsum, cstate, odone, members, moffs;
     void *nccl_comm = nullptr;       // ncclComm_t of the oversized-frame split (gsc_split_comm_init)
     int nccl_ranks = 1, nccl_rank = 0;
     unsigned debug = 0;              // GSC_DBG_* (gsc_ctx_set_debug): cross-check paths for the parity tests
@@ -204,7 +204,7 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
                       &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr, &c->scompact, &c->soffs,
-                      &c->perm, &c->pns, &c->xs, &c->blo, &c->bhi, &c->wsum, &c->cstate, &c->odone};
+                      &c->perm, &c->pns, &c->xs, &c->blo, &c->bhi, &c->wsum, &c->cstate, &c->odone, &c->members, &c->moffs};
     for (DevBuf *b : bufs) b->release();
     c->hsizes.release();
     c->hpcm.release();
@@ -417,7 +417,7 @@ static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
     TRY(c->blo.ensure(4 * nwin)); TRY(c->bhi.ensure(4 * nwin)); TRY(c->wsum.ensure(16 * nwin));
     LAUNCH(c, k_seed_prep<D>, c->F, 512, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->pnorm.as<float>(),
            c->perm.as<int>(), c->pns.as<float>(), c->xs.as<float>(), c->blo.as<float>(), c->bhi.as<float>());
-    static const int seed_t = [] { const char *e = getenv("GSC_SEED_T"); const int x = e ? atoi(e) : 128; return (x == 64 || x == 256) ? x : 128; }();
+    static const int seed_t = [] { const char *e = getenv("GSC_SEED_T"); const int x = e ? atoi(e) : 256; return (x == 64 || x == 128) ? x : 256; }();   // measured at 592 frames: 64 -> 1133 ms, 128 -> 790 ms, 256 -> 628 ms
 #define GSC_SEED2_LAUNCH(TT)                                                                                              \
     do {                                                                                                                  \
         SMEM_OPTIN((k_seed2<D, TT>), smem);                                                                               \
@@ -428,9 +428,17 @@ static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
                c->sdbg.as<unsigned long long>());                                                                         \
     } while (0)
     if (seed_t == 64) GSC_SEED2_LAUNCH(64);
-    else if (seed_t == 256) GSC_SEED2_LAUNCH(256);
-    else GSC_SEED2_LAUNCH(128);
+    else if (seed_t == 128) GSC_SEED2_LAUNCH(128);
+    else GSC_SEED2_LAUNCH(256);
 #undef GSC_SEED2_LAUNCH
+    return GSC_OK;
+}
+
+// members of every cluster in ascending point order (k_group_labels) for the label array `lab`
+static int stage_group(gsc_ctx *c, const int *lab) {
+    TRY(c->members.ensure(4 * (size_t)c->sumN)); TRY(c->moffs.ensure(4 * (size_t)c->F * (c->Kmax + 1)));
+    const size_t smem = 4 * ((size_t)c->Kmax + 1);
+    LAUNCH(c, k_group_labels, c->F, 32, smem, c->frames.as<GscFrame>(), lab, c->members.as<int>(), c->moffs.as<int>(), c->Kmax);
     return GSC_OK;
 }
 
@@ -442,9 +450,16 @@ static int stage_seed(gsc_ctx *c, int D, int init_type, bool want_seeds) {
     TRY(c->cnt0.ensure(4 * fk));
     if (want_seeds) TRY(c->seeds.ensure(4 * fk));
     DISPATCH_D(D, TRY(seed_launch<D>(c, init_type, want_seeds)));
-    dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
-    DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
-                         c->sid.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), c->Kmax));
+    if (c->debug & GSC_DBG_LABEL_SCAN) {   // the O(K*N) label scan per cluster (cross-check)
+        dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
+        DISPATCH_D(D, LAUNCH(c, k_owner_sums_f<D>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
+                             c->sid.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), c->Kmax));
+    } else {
+        TRY(stage_group(c, c->sid.as<int>()));
+        dim3 g2((c->Kmax + 127) / 128, c->F);
+        DISPATCH_D(D, LAUNCH(c, k_member_sums_f<D>, g2, 128, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),
+                             c->members.as<int>(), c->moffs.as<int>(), c->sums.as<float>(), c->cnt0.as<int>(), c->Kmax));
+    }
     dim3 g3((c->Kmax + 255) / 256, c->F);
     DISPATCH_D(D, LAUNCH(c, k_means_from_sums<D>, g3, 256, 0, c->frames.as<GscFrame>(), c->sums.as<float>(),
                          c->cnt0.as<int>(), c->cen.as<float>(), c->Kmax, 0));
@@ -588,10 +603,18 @@ static int stage_dictionary(gsc_ctx *c, bool want_entry) {
     TRY(c->order.ensure(4 * fk)); TRY(c->counts.ensure(4 * fk)); TRY(c->dict.ensure(2 * fk * cs));
     TRY(c->datten.ensure(fk)); TRY(c->dattr.ensure(fk));
     if (want_entry) TRY(c->entry.ensure(4 * (size_t)c->sumN));
-    dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
-    DISPATCH_CS(cs, LAUNCH(c, k_class_means<CS>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
-                           c->attr.as<unsigned char>(), c->labels.as<int>(), c->means0.as<float>(), c->cnt0.as<int>(),
-                           c->Kmax));
+    if (c->debug & GSC_DBG_LABEL_SCAN) {   // the O(K*N) label scan per cluster (cross-check)
+        dim3 g2((c->Kmax + GSC_OWNER_THREADS - 1) / GSC_OWNER_THREADS, c->F);
+        DISPATCH_CS(cs, LAUNCH(c, k_class_means<CS>, g2, GSC_OWNER_THREADS, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
+                               c->attr.as<unsigned char>(), c->labels.as<int>(), c->means0.as<float>(), c->cnt0.as<int>(),
+                               c->Kmax));
+    } else {
+        TRY(stage_group(c, c->labels.as<int>()));
+        dim3 g2((c->Kmax + 127) / 128, c->F);
+        DISPATCH_CS(cs, LAUNCH(c, k_class_means_members<CS>, g2, 128, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
+                               c->attr.as<unsigned char>(), c->members.as<int>(), c->moffs.as<int>(), c->means0.as<float>(),
+                               c->cnt0.as<int>(), c->Kmax));
+    }
     size_t smem = sizeof(int) * 4 * (size_t)c->Kmax;
     DISPATCH_CS(cs, {
         SMEM_OPTIN(k_dictionary<CS>, smem);
@@ -939,6 +962,7 @@ extern "C" int gsc_split_comm_destroy(gsc_ctx *c) {
     return GSC_OK;
 }
 
+#define GSC_SPLIT_SEED_MAX (1 << 19)
 // Start centroids for the split: yakmo's k-means++ (k_seed2, exact) on rank 0's shard, its seed rows broadcast to
 // every rank.  (The reference seeds over the whole frame; a frame that does not fit one GPU has no single place
 // where that prefix sum could run, so the split's start is the seeding of the first shard -- a documented
@@ -947,6 +971,9 @@ extern "C" int gsc_split_seed(gsc_ctx *c, const float *X, int N, int D, int K, f
     FpGuard g;
     if (!c || !centroids) return set_err(GSC_ERR_ARG, "null argument");
     if (K > N) return set_err(GSC_ERR_ARG, "k (%d) > rows of the shard (%d)", K, N);
+    // the seeding kernel keeps per-point / per-window state of ONE frame in shared memory: seed on the first
+    // GSC_SPLIT_SEED_MAX rows of the shard
+    if (N > GSC_SPLIT_SEED_MAX) N = GSC_SPLIT_SEED_MAX;
     TRY(upload_points(c, X, N, D, K));
     TRY(c->cen.ensure(4 * (size_t)K * D));
     if (c->nccl_rank == 0) {

@@ -665,6 +665,89 @@ __global__ void __launch_bounds__(GSC_OWNER_THREADS) k_owner_sums_f(const GscFra
     }
 }
 
+// ---------------------------------------------------------------------------
+// Members of every cluster in ascending point order, in O(N): one warp per frame.
+//   pass 1  counts per label (shared-memory histogram)
+//   pass 2  exclusive scan -> offs[0..K]
+//   pass 3  STABLE scatter, 32 points at a time: __match_any_sync groups the lanes with the same label, a lane's rank
+//           inside its group is the number of lower lanes in it, the group's lowest lane advances the label's
+//           cursor -- groups are taken in point order and lanes in lane order, so every cluster's members come out
+//           in ascending j, the order in which the reference sums them (enc:845-864, yakmo's last init step).
+// The per-cluster sums that used to scan all N labels per cluster (O(K*N)) walk these lists instead.
+// grid = F, block = 32, dynamic smem = 4 * (K + 1) bytes.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_group_labels(const GscFrame *__restrict__ frames, const int *__restrict__ labels,
+                                                     int *__restrict__ members,   // [sumN] point indices grouped by label
+                                                     int *__restrict__ offs,      // [F][Kmax+1]
+                                                     int Kmax) {
+    extern __shared__ int s_cur[];   // [K+1]
+    constexpr unsigned FULL = 0xffffffffu;
+    const GscFrame f = frames[blockIdx.x];
+    const int K = f.K, N = f.N, lane = threadIdx.x;
+    if (K <= 0) return;
+    const int *lab = labels + f.chunk_off;
+    int *mem = members + f.chunk_off;
+    int *of = offs + (long long)f.slot * (Kmax + 1);
+    for (int c = lane; c <= K; c += 32) s_cur[c] = 0;
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) {
+        const int l = lab[j];
+        if (l >= 0 && l < K) atomicAdd(&s_cur[l], 1);
+    }
+    __syncwarp();
+    // exclusive scan of the K counts: a contiguous stretch per lane, then the lanes' totals
+    const int per = (K + 31) / 32, c0 = lane * per, c1 = min(K, c0 + per);
+    int tot = 0;
+    for (int c = c0; c < c1; ++c) tot += s_cur[c];
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    int run = incl - tot;
+    for (int c = c0; c < c1; ++c) { const int n = s_cur[c]; s_cur[c] = run; of[c] = run; run += n; }
+    if (lane == 31) { s_cur[K] = incl; of[K] = incl; }
+    __syncwarp();
+    for (int base = 0; base < N; base += 32) {
+        const int j = base + lane;
+        int l = (j < N) ? lab[j] : -1;
+        if (l < 0 || l >= K) l = -1 - lane;                 // invalid / past the end: a group of its own, not stored
+        const unsigned grp = __match_any_sync(FULL, l);
+        const int leader = __ffs(grp) - 1, rank = __popc(grp & ((1u << lane) - 1u));
+        int basep = 0;
+        if (lane == leader && l >= 0) { basep = s_cur[l]; s_cur[l] = basep + __popc(grp); }
+        basep = __shfl_sync(FULL, basep, leader);
+        if (l >= 0) mem[basep + rank] = j;
+        __syncwarp();
+    }
+}
+
+// Float sums of the feature rows of every cluster's members in point order (yakmo init(): the last seed adds each
+// point to its cell; Lloyd-style mean update of run()): thread per cluster over its member list.
+template <int D>
+__global__ void __launch_bounds__(128) k_member_sums_f(const GscFrame *__restrict__ frames, const float *__restrict__ X,
+                                                       const int *__restrict__ members, const int *__restrict__ offs,
+                                                       float *__restrict__ sums, int *__restrict__ counts, int Kmax) {
+    const GscFrame f = frames[blockIdx.y];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= f.K) return;
+    const float *Xf = X + f.chunk_off * D;
+    const int *mem = members + f.chunk_off;
+    const int *of = offs + (long long)f.slot * (Kmax + 1);
+    const int a = of[c], b = of[c + 1];
+    float acc[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) acc[k] = 0.0f;
+    for (int t = a; t < b; ++t) {
+        float p[D];
+        gsc_load_row<D>(Xf, mem[t], p);
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc[k] = acc[k] + p[k];
+    }
+    float *o = sums + ((long long)f.slot * Kmax + c) * D;
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = acc[k];
+    counts[(long long)f.slot * Kmax + c] = b - a;
+}
+
 // centroid = sum / (float)count  (run() RVA 0x2290-0x22d3; 0/0 -> NaN kept).
 // keep_empty: Lloyd variant keeps the previous centroid for empty clusters.
 template <int D>
@@ -810,6 +893,42 @@ __global__ void __launch_bounds__(GSC_OWNER_THREADS) k_class_means(const GscFram
         for (int k = 0; k < CS; ++k) o[k] = (float)((fabs(y) <= 1e-12) ? 0.0 : acc[k] / y);  // div0, enc:863
         counts[(long long)f.slot * Kmax + c] = cnt;
     }
+}
+
+// enc:845-864 over the member lists of k_group_labels: Double accumulate in ascending point order, Single store via div0.
+template <int CS>
+__global__ void __launch_bounds__(128) k_class_means_members(const GscFrame *__restrict__ frames, const short *__restrict__ pcm,
+                                                             const unsigned char *__restrict__ attr,
+                                                             const int *__restrict__ members, const int *__restrict__ offs,
+                                                             float *__restrict__ means0, int *__restrict__ counts, int Kmax) {
+    const GscFrame f = frames[blockIdx.y];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= f.K) return;
+    const int *mem = members + f.chunk_off;
+    const unsigned char *at = attr + f.chunk_off;
+    const int *of = offs + (long long)f.slot * (Kmax + 1);
+    const int a0 = of[c], b0 = of[c + 1];
+    double acc[CS];
+#pragma unroll
+    for (int k = 0; k < CS; ++k) acc[k] = 0.0;
+    for (int t = a0; t < b0; ++t) {
+        const int n = mem[t];
+        const int i = n / f.C, ch = n - i * f.C;
+        const short *row = pcm + f.pcm_off + (long long)ch * f.stride + (long long)i * CS;
+        const unsigned char a = at[n];
+        const bool rv = a & 1, ng = (a >> 1) & 1;
+#pragma unroll
+        for (int k = 0; k < CS; ++k) {
+            const int p = rv ? CS - 1 - k : k;
+            const double x = (i * CS + p < f.S) ? gsc_sample(row[p]) : 0.0;
+            acc[k] += x * (ng ? -1.0 : 1.0);  // enc:857
+        }
+    }
+    float *o = means0 + ((long long)f.slot * Kmax + c) * CS;
+    const double y = (double)(b0 - a0);
+#pragma unroll
+    for (int k = 0; k < CS; ++k) o[k] = (float)((fabs(y) <= 1e-12) ? 0.0 : acc[k] / y);  // div0, enc:863
+    counts[(long long)f.slot * Kmax + c] = b0 - a0;
 }
 
 // ---------------------------------------------------------------------------

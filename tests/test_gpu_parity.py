@@ -399,3 +399,21 @@ def test_legacy_ann_sees_the_callers_live_rows(ctx, oracle):
         kdt.close()
     assert np.array_equal(labels, want[1]) and np.array_equal(cen.view(np.uint32), want[0].view(np.uint32))
     assert err == want[3]
+
+
+def test_member_lists_equal_label_scans(ctx, oracle):
+    """Per-cluster sums over the stable member lists (k_group_labels, O(N)) == the per-cluster scans of all labels
+    (O(K*N), GSC_DBG_LABEL_SCAN), on a frame with heavily skewed clusters (long silent stretch)."""
+    pcm = _quiet(_audio(0.6, 44100, 2, 21)).copy()
+    pcm[:, 5000:14000] = 0
+    a = ctx.encode_frames([pcm], chunk_bit_depth=12, chunks_per_frame=1024)[0]
+    sa, _ = ctx.fetch_stream(1, 44100)
+    ctx.set_debug(ctx.DBG_LABEL_SCAN)
+    try:
+        b = ctx.encode_frames([pcm], chunk_bit_depth=12, chunks_per_frame=1024)[0]
+        sb, _ = ctx.fetch_stream(1, 44100)
+    finally:
+        ctx.set_debug(0)
+    assert (a.R, a.passes, a.err) == (b.R, b.passes, b.err) and sa == sb
+    ref = oracle.encode_frame(pcm, chunk_bit_depth=12, chunks_per_frame=1024, band_all=1)
+    assert sa == oracle.write_frame(ref, 2, 4, 12, 44100)
