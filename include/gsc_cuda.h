@@ -286,7 +286,10 @@ int gsc_fetch_quality(gsc_ctx *ctx, int n_frames, uint64_t *sq_err, int64_t *sam
 #define GSC_DBG_LLOYD_OWNER   16u  /* Lloyd update by per-cluster owner threads (ordered sums) instead of the scatter */
 #define GSC_DBG_ONLINE_BATCHED 32u /* K <= 256: the batched CTA-per-frame kernel instead of the warp-per-frame one */
 #define GSC_DBG_LABEL_SCAN     64u /* per-cluster sums by scanning all labels per cluster (O(K*N)) instead of member lists */
+#define GSC_DBG_DIVIDER_V1     128u /* FindAttenuationDivider with the per-thread loop that divides in the inner loop */
 int gsc_ctx_set_debug(gsc_ctx *ctx, unsigned flags);
+/* Exhaustive self-check of the tabulated-reciprocal division used by the attenuation-divider kernel at `bits`. */
+int gsc_selftest_divider_division(gsc_ctx *ctx, int bits, uint64_t *mismatches);
 /* Debug: counters of the last online k-means launch, 16 x uint64 per frame:
  * batches, points, re-filtered points, resolver rounds, full candidate lists,
  * candidates (lane 0); rest reserved (zero). */

@@ -28,7 +28,7 @@ EXPORTS = [
     "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end",
     "gsc_split_unique_id", "gsc_split_comm_init", "gsc_split_comm_destroy", "gsc_split_seed", "gsc_split_lloyd", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_ctx_set_debug", "gsc_debug_online_counters", "gsc_debug_seed_counters",
+    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_ctx_set_debug", "gsc_selftest_divider_division", "gsc_debug_online_counters", "gsc_debug_seed_counters",
 ]
 
 
@@ -200,11 +200,16 @@ class Context:
         self._ck(self.L.gsc_debug_online_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
 
-    DBG_ONLINE_EXACT, DBG_SEED_FULLSCAN, DBG_SEED_SERIAL, DBG_KNNFIT_DENSE, DBG_LLOYD_OWNER, DBG_ONLINE_BATCHED, DBG_LABEL_SCAN = 1, 2, 4, 8, 16, 32, 64
+    DBG_ONLINE_EXACT, DBG_SEED_FULLSCAN, DBG_SEED_SERIAL, DBG_KNNFIT_DENSE, DBG_LLOYD_OWNER, DBG_ONLINE_BATCHED, DBG_LABEL_SCAN, DBG_DIVIDER_V1 = 1, 2, 4, 8, 16, 32, 64, 128
 
     def set_debug(self, flags: int):
         """Cross-check paths (include/gsc_cuda.h GSC_DBG_*); 0 = the product path."""
         self._ck(self.L.gsc_ctx_set_debug(C.c_void_p(self.h), C.c_uint(flags)))
+
+    def selftest_divider_division(self, bits: int) -> int:
+        v = C.c_uint64(0)
+        self._ck(self.L.gsc_selftest_divider_division(C.c_void_p(self.h), bits, C.byref(v)))
+        return int(v.value)
 
     def seed_counters(self, n_frames: int) -> np.ndarray:
         out = np.zeros((n_frames, 8), np.uint64)

@@ -354,8 +354,12 @@ static int upload_frames(gsc_ctx *c) {
 static int stage_divider(gsc_ctx *c, bool want_v) {
     TRY(c->divider.ensure(sizeof(int) * c->F));
     if (want_v) TRY(c->vout.ensure(sizeof(double) * 64 * c->F));
-    DISPATCH_CS(c->cs, LAUNCH(c, k_find_divider<CS>, c->F, 64, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
-                              c->bits, c->divider.as<int>(), want_v ? c->vout.as<double>() : nullptr));
+    if (c->debug & GSC_DBG_DIVIDER_V1)
+        DISPATCH_CS(c->cs, LAUNCH(c, k_find_divider<CS>, c->F, 64, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
+                                  c->bits, c->divider.as<int>(), want_v ? c->vout.as<double>() : nullptr));
+    else
+        DISPATCH_CS(c->cs, LAUNCH(c, k_find_divider2<CS>, c->F, 64, 0, c->frames.as<GscFrame>(), c->pcm.as<short>(),
+                                  c->bits, c->divider.as<int>(), want_v ? c->vout.as<double>() : nullptr));
     return GSC_OK;
 }
 
@@ -1492,6 +1496,22 @@ extern "C" int gsc_log_array(gsc_ctx *c, const double *x, int64_t n, double *y) 
     LAUNCH(c, k_log_array, (unsigned)((n + 255) / 256), 256, 0, dx, dy, (long long)n);
     TRY(d2h(c, y, dy, 8 * (size_t)n));
     return sync(c);
+}
+
+// Exhaustive self-check of the tabulated-reciprocal division of k_find_divider2 (all dividers, attenuations and
+// quantised samples of the bit depth): *mismatches must come back 0.
+extern "C" int gsc_selftest_divider_division(gsc_ctx *c, int bits, uint64_t *mismatches) {
+    FpGuard g;
+    if (!c || !mismatches || bits < 2 || bits > 16) return set_err(GSC_ERR_ARG, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    TRY(c->misc.ensure(8));
+    CU(cudaMemsetAsync(c->misc.p, 0, 8, c->stream));
+    LAUNCH(c, k_check_divider_division, 64, 256, 0, bits, c->misc.as<unsigned long long>());
+    unsigned long long v = 0;
+    TRY(d2h(c, &v, c->misc.p, 8));
+    TRY(sync(c));
+    *mismatches = v;
+    return GSC_OK;
 }
 
 extern "C" int gsc_fp32_peak_probe(gsc_ctx *c, double *tflops) {

@@ -88,6 +88,122 @@ __global__ void __launch_bounds__(64) k_find_divider(const GscFrame *__restrict_
 }
 
 // ---------------------------------------------------------------------------
+// K2, second form.  Same contract (thread t = divider t+1, its Double sum formed in the reference's order), with the
+// work that does not depend on the divider done once per CTA and the divisions taken out of the inner loop:
+//   * a tile of 64 chunks is converted to Double (x = s / 32767.0, enc:1645) and its chunk peaks hi (enc:1687-1690)
+//     computed cooperatively, then every divider thread reads them as shared-memory broadcasts;
+//   * ComputeAttenuation's loop "first r with hi * T[r] > 32767" (enc:1692-1697) is monotone in hi, so each divider
+//     tabulates hmax[r] = the largest integer hi that does NOT trip r (found with the very same Double predicate) and
+//     the per-chunk attenuation is a 4-step search over integers;
+//   * makeFloatSample's division q / (obd * coeff) (enc:1676) has only 16 distinct divisors per divider: with
+//     R = RN(1 / y) tabulated, q0 = RN(q R), r = fma(-q0, y, q) (exact), q1 = fma(r, R, q0) is the correctly rounded
+//     quotient (Markstein); k_check_divider_division verifies it against the hardware division for EVERY
+//     (divider, attenuation, q) that can occur at 8 and 12 bits (the test runs it), other bit depths divide.
+// ---------------------------------------------------------------------------
+#define GSC_DIV_TILE 64
+__device__ __forceinline__ double gsc_div_markstein(double q, double y, double R) {
+    const double q0 = q * R;
+    const double r = fma(-q0, y, q);
+    return fma(r, R, q0);
+}
+
+template <int CS>
+__global__ void __launch_bounds__(64) k_find_divider2(const GscFrame *__restrict__ frames, const short *__restrict__ pcm,
+                                                      int bits, int *__restrict__ divider_out, double *__restrict__ v_out) {
+    __shared__ double s_x[GSC_DIV_TILE * CS];
+    __shared__ int s_hi[GSC_DIV_TILE];
+    __shared__ double s_T[GSC_MAX_ATT + 2][64];   // coeff table of every divider, [r][divider]: conflict-free
+    __shared__ double s_Y[GSC_MAX_ATT + 1][64];   // obd * coeff
+    __shared__ double s_R[GSC_MAX_ATT + 1][64];   // RN(1 / (obd * coeff))
+    __shared__ int s_hmax[GSC_MAX_ATT + 2][64];
+    __shared__ double sv[64];
+    const GscFrame f = frames[blockIdx.x];
+    const int t = threadIdx.x;
+    const double law = 1.0 / (double)(t + 1);
+    const int obd = (1 << (bits - 1)) - 1;
+    const bool fastdiv = (bits == 8 || bits == 12);
+    {
+        double c = 1.0 + 0.0 * law;
+        s_T[0][t] = c;
+        for (int r = 1; r <= GSC_MAX_ATT + 1; ++r) { c = c + (double)r * law; s_T[r][t] = c; }
+        for (int a = 0; a <= GSC_MAX_ATT; ++a) { const double y = (double)obd * s_T[a][t]; s_Y[a][t] = y; s_R[a][t] = 1.0 / y; }
+        for (int r = 1; r <= GSC_MAX_ATT + 1; ++r) {       // largest hi in [0, 32768] with !(hi * T[r] > 32767)
+            const double T = s_T[r][t];
+            int lo = 0, hi = 32769;                        // predicate false at lo (0 * T = 0), true at 32769 (T >= 1)
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((double)mid * T > 32767.0) hi = mid; else lo = mid; }
+            s_hmax[r][t] = lo;
+        }
+    }
+    double v = 0.0;
+    const int nchunks = f.S / CS;
+    for (int j = 0; j < f.C; ++j) {
+        const short *row = pcm + f.pcm_off + (long long)j * f.stride;
+        for (int k0 = 0; k0 < nchunks; k0 += GSC_DIV_TILE) {
+            const int tc = min(GSC_DIV_TILE, nchunks - k0);
+            __syncthreads();
+            for (int e = t; e < tc * CS; e += 64) s_x[e] = gsc_sample(row[(long long)k0 * CS + e]);
+            __syncthreads();
+            if (t < tc) {
+                int hi = 0;
+#pragma unroll
+                for (int l = 0; l < CS; ++l) { const int h = gsc_hi(s_x[t * CS + l]); hi = h > hi ? h : hi; }
+                s_hi[t] = hi;
+            }
+            __syncthreads();
+            for (int k = 0; k < tc; ++k) {
+                const int hi = s_hi[k];
+                // attenuation: first r in 1..15 with hi > hmax[r] (else 16), minus one  (enc:1692-1697)
+                int lo_r = 1, hi_r = GSC_MAX_ATT + 1;
+                while (lo_r < hi_r) { const int mid = (lo_r + hi_r) >> 1; if (hi > s_hmax[mid][t]) hi_r = mid; else lo_r = mid + 1; }
+                const int a = lo_r - 1;
+                const double coeff = s_T[a][t], y = s_Y[a][t], R = s_R[a][t];
+#pragma unroll
+                for (int l = 0; l < CS; ++l) {
+                    const double x = s_x[k * CS + l];
+                    const short os = gsc_quant(x, obd, coeff, false);
+                    double fs = fastdiv ? gsc_div_markstein((double)os, y, R) : (double)os / y;
+                    if (fs < -1.0) fs = -1.0;
+                    if (fs > 1.0) fs = 1.0;
+                    const double d = x - fs;
+                    v += d * d;
+                }
+            }
+        }
+    }
+    sv[t] = v;
+    if (v_out) v_out[(long long)f.slot * 64 + t] = v;
+    __syncthreads();
+    if (t == 0) {
+        int bestDiv = 1;
+        double best = 3.40282346638528860e+38;  // MaxSingle, enc:575
+        for (int i = 0; i < 64; ++i)
+            if (sv[i] < best) { best = sv[i]; bestDiv = i + 1; }
+        divider_out[f.slot] = bestDiv;
+    }
+}
+
+// Exhaustive check of gsc_div_markstein against the division it replaces: every divider 1..64, attenuation 0..15 and
+// quantised sample -obd..obd at the given bit depth.  out[0] += mismatches (bit patterns compared).
+__global__ void k_check_divider_division(int bits, unsigned long long *__restrict__ out) {
+    const int t = blockIdx.x;                  // divider t+1
+    const double law = 1.0 / (double)(t + 1);
+    const int obd = (1 << (bits - 1)) - 1;
+    double T[GSC_MAX_ATT + 1];
+    double c = 1.0 + 0.0 * law;
+    T[0] = c;
+    for (int r = 1; r <= GSC_MAX_ATT; ++r) { c = c + (double)r * law; T[r] = c; }
+    unsigned long long bad = 0;
+    for (int a = 0; a <= GSC_MAX_ATT; ++a) {
+        const double y = (double)obd * T[a], R = 1.0 / y;
+        for (int q = -obd + (int)threadIdx.x; q <= obd; q += blockDim.x) {
+            const double want = (double)q / y, got = gsc_div_markstein((double)q, y, R);
+            bad += (__double_as_longlong(want) != __double_as_longlong(got));
+        }
+    }
+    if (bad) atomicAdd(out, bad);
+}
+
+// ---------------------------------------------------------------------------
 // K1  chunk extraction, heuristic attributes, features (enc:467-485)
 // One thread per chunk.  grid = (ceil(maxN/256), F).
 // ---------------------------------------------------------------------------

@@ -417,3 +417,21 @@ def test_member_lists_equal_label_scans(ctx, oracle):
     assert (a.R, a.passes, a.err) == (b.R, b.passes, b.err) and sa == sb
     ref = oracle.encode_frame(pcm, chunk_bit_depth=12, chunks_per_frame=1024, band_all=1)
     assert sa == oracle.write_frame(ref, 2, 4, 12, 44100)
+
+
+def test_divider_kernel_forms_agree(ctx, oracle):
+    """k_find_divider2 (tabulated reciprocals, integer attenuation thresholds) == the straightforward kernel == the
+    oracle, all 64 Double sums bit for bit; the reciprocal division is checked exhaustively."""
+    assert ctx.selftest_divider_division(8) == 0 and ctx.selftest_divider_division(12) == 0
+    for ch, bits, seed in [(1, 12, 1), (2, 8, 2), (2, 12, 3)]:
+        pcm = _audio(0.4, 44100, ch, seed)          # full-scale: exercises the low attenuations and the clamps
+        d_ref, v_ref = oracle.find_attenuation_divider(pcm, 4, bits, return_v=True)
+        d2, v2 = ctx.find_attenuation_divider(pcm, 4, bits, return_v=True)
+        ctx.set_debug(ctx.DBG_DIVIDER_V1)
+        try:
+            d1, v1 = ctx.find_attenuation_divider(pcm, 4, bits, return_v=True)
+        finally:
+            ctx.set_debug(0)
+        assert d1 == d2 == d_ref and np.array_equal(v1, v_ref) and np.array_equal(v2, v_ref)
+    v10 = ctx.find_attenuation_divider(_quiet(_audio(0.2, 44100, 1, 4)), 4, 10, return_v=True)   # other depth: plain division
+    assert v10[0] == oracle.find_attenuation_divider(_quiet(_audio(0.2, 44100, 1, 4)), 4, 10)
