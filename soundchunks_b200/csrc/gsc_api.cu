@@ -123,7 +123,7 @@ struct gsc_ctx {
     DevBuf frames, pcm, divider, vout, attr, atten, feat, dst, pnorm, up, r, sid, seeds, cen, cnorm,
         sums, cnt0, labels, passes, err, means0, means, order, counts, dict, datten, dattr, entry, best,
         use, band, overfull, remap, order2, newR, odict, odatten, oindex, oattr, dist, misc, dbg, sdbg, kv, kn, ke, sbytes, snb, sqerr,
-        perm, pns, xs, blo, bhi, wsum, cstate, odone, members, moffs;
+        perm, pns, xs, blo, bhi, wsum, cstate, odone, members, moffs, cenh;
     void *nccl_comm = nullptr;       // ncclComm_t of the oversized-frame split (gsc_split_comm_init)
     int nccl_ranks = 1, nccl_rank = 0;
     unsigned debug = 0;              // GSC_DBG_* (gsc_ctx_set_debug): cross-check paths for the parity tests
@@ -204,7 +204,7 @@ extern "C" void gsc_destroy(gsc_ctx *c) {
                       &c->labels, &c->passes, &c->err, &c->means0, &c->means, &c->order, &c->counts, &c->dict,
                       &c->datten, &c->dattr, &c->entry, &c->best, &c->use, &c->band, &c->overfull, &c->remap,
                       &c->order2, &c->newR, &c->odict, &c->odatten, &c->oindex, &c->oattr, &c->dist, &c->misc, &c->dbg, &c->sdbg, &c->kv, &c->kn, &c->ke, &c->sbytes, &c->snb, &c->sqerr, &c->scompact, &c->soffs,
-                      &c->perm, &c->pns, &c->xs, &c->blo, &c->bhi, &c->wsum, &c->cstate, &c->odone, &c->members, &c->moffs};
+                      &c->perm, &c->pns, &c->xs, &c->blo, &c->bhi, &c->wsum, &c->cstate, &c->odone, &c->members, &c->moffs, &c->cenh};
     for (DevBuf *b : bufs) b->release();
     c->hsizes.release();
     c->hpcm.release();
@@ -421,19 +421,27 @@ static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
     TRY(c->blo.ensure(4 * nwin)); TRY(c->bhi.ensure(4 * nwin)); TRY(c->wsum.ensure(16 * nwin));
     LAUNCH(c, k_seed_prep<D>, c->F, 512, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->pnorm.as<float>(),
            c->perm.as<int>(), c->pns.as<float>(), c->xs.as<float>(), c->blo.as<float>(), c->bhi.as<float>());
-    static const int seed_t = [] { const char *e = getenv("GSC_SEED_T"); const int x = e ? atoi(e) : 256; return (x == 64 || x == 128) ? x : 256; }();   // measured at 592 frames: 64 -> 1133 ms, 128 -> 790 ms, 256 -> 628 ms
-#define GSC_SEED2_LAUNCH(TT)                                                                                              \
+    // CTA shape: threads x resident CTAs per SM the register allocation is sized for (GSC_SEED_SHAPE = "256x2" ...)
+    static const int seed_shape = [] {
+        const char *e = getenv("GSC_SEED_SHAPE");
+        if (e && !strcmp(e, "256x3")) return 1;
+        if (e && !strcmp(e, "128x4")) return 2;
+        if (e && !strcmp(e, "128x6")) return 3;
+        return 0;
+    }();
+#define GSC_SEED2_LAUNCH(TT, MB)                                                                                          \
     do {                                                                                                                  \
-        SMEM_OPTIN((k_seed2<D, TT>), smem);                                                                               \
-        LAUNCH(c, (k_seed2<D, TT>), c->F, TT, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->xs.as<float>(),     \
+        SMEM_OPTIN((k_seed2<D, TT, MB>), smem);                                                                           \
+        LAUNCH(c, (k_seed2<D, TT, MB>), c->F, TT, smem, c->frames.as<GscFrame>(), c->feat.as<float>(), c->xs.as<float>(), \
                c->pns.as<float>(), c->perm.as<int>(), c->blo.as<float>(), c->bhi.as<float>(), init_type,                  \
                c->r.as<float>(), c->up.as<float>(), c->sid.as<int>(), c->wsum.as<int4>(),                                 \
                want_seeds ? c->seeds.as<int>() : nullptr, c->cen.as<float>(), c->cnorm.as<float>(), c->Kmax,              \
                c->sdbg.as<unsigned long long>());                                                                         \
     } while (0)
-    if (seed_t == 64) GSC_SEED2_LAUNCH(64);
-    else if (seed_t == 128) GSC_SEED2_LAUNCH(128);
-    else GSC_SEED2_LAUNCH(256);
+    if (seed_shape == 1) GSC_SEED2_LAUNCH(256, 3);
+    else if (seed_shape == 2) GSC_SEED2_LAUNCH(128, 4);
+    else if (seed_shape == 3) GSC_SEED2_LAUNCH(128, 6);
+    else GSC_SEED2_LAUNCH(256, 2);
 #undef GSC_SEED2_LAUNCH
     return GSC_OK;
 }
@@ -473,9 +481,13 @@ static int stage_seed(gsc_ctx *c, int D, int init_type, bool want_seeds) {
 static int stage_assign(gsc_ctx *c, int D, bool want_dist) {
     TRY(c->labels.ensure(4 * (size_t)c->sumN));
     if (want_dist) TRY(c->dist.ensure(4 * (size_t)c->sumN));
+    const int Kpad = (c->Kmax + 3) & ~3;
+    TRY(c->cenh.ensure(4 * (size_t)c->F * Kpad));
+    dim3 gh((Kpad + 255) / 256, c->F);
+    DISPATCH_D(D, LAUNCH(c, k_cen_h<D>, gh, 256, 0, c->frames.as<GscFrame>(), c->cen.as<float>(), c->cenh.as<float>(), c->Kmax, Kpad));
     dim3 grid((c->maxN + GSC_ASSIGN_T * GSC_ASSIGN_P - 1) / (GSC_ASSIGN_T * GSC_ASSIGN_P), c->F);
     DISPATCH_D(D, LAUNCH(c, k_assign<D>, grid, GSC_ASSIGN_T, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
-                         c->labels.as<int>(), want_dist ? c->dist.as<float>() : nullptr, c->Kmax));
+                         c->cenh.as<float>(), c->labels.as<int>(), want_dist ? c->dist.as<float>() : nullptr, c->Kmax, Kpad));
     return GSC_OK;
 }
 

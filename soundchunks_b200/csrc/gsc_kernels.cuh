@@ -1671,29 +1671,95 @@ __device__ __forceinline__ unsigned long long gsc_a_ffma2(unsigned long long a, 
     unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
 
+// ---- 1-D bulk copies (TMA, cp.async.bulk) + mbarrier: the codebook tiles of k_assign ----
+__device__ __forceinline__ unsigned gsc_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gsc_mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gsc_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gsc_mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gsc_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gsc_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gsc_smem_addr(dst)), "l"(src), "r"(bytes), "r"(gsc_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void gsc_mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "GSC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra GSC_DONE_%=;\n"
+        "bra GSC_WAIT_%=;\n"
+        "GSC_DONE_%=:\n"
+        "}\n" ::"r"(gsc_smem_addr(bar)), "r"(parity) : "memory");
+}
+
+// h_c = -0.5 |c|^2 (1 - g) over the bound's dimensions, for every centroid of every frame (rows padded to a multiple
+// of 4 per frame so that a tile of them is a legal bulk copy; the pad never wins: NaN)
+template <int D>
+__global__ void k_cen_h(const GscFrame *__restrict__ frames, const float *__restrict__ cen, float *__restrict__ ch, int Kmax, int Kpad) {
+    constexpr int DF = (D >= 8) ? D / 2 : D;
+    const GscFrame f = frames[blockIdx.y];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Kpad) return;
+    float h = __int_as_float(0x7fc00000);
+    if (c < f.K) {
+        const float *r = cen + ((long long)f.slot * Kmax + c) * D;
+        float nc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DF; ++k) nc = fmaf(r[k], r[k], nc);
+        h = -0.5f * nc * (1.0f - GSC_LB_GAMMA);
+    }
+    ch[(long long)f.slot * Kpad + c] = h;
+}
+
 // Register tile: 8 points per thread held as 4 packed pairs, so one FFMA2 (fma.rn.f32x2) advances the
-// lower-bound score of two points; the codebook tile is read from shared memory with broadcast loads
-// (2 x LDS.128 + 1 x LDS.32 per centroid for 64 FMAs).  Per (point, centroid): 8 FMAs + 1 compare; the exact
-// ANN-order distance is evaluated only for centroids whose certified lower bound does not exceed the point's
-// current best, so the result is the exact argmin (lowest index on ties).
+// lower-bound score of two points; the codebook streams through shared memory in tiles of 512 centroids (rows 16 KB
+// + h 2 KB) that ONE thread requests with bulk async copies (TMA, cp.async.bulk) into a two-deep ring: the copy of
+// tile t+1 is in flight while tile t is scored, its arrival is an mbarrier phase, and the only block barrier left per
+// tile is the one that frees a buffer.  Tile reads are broadcast loads (2 x LDS.128 + 1 x LDS.32 per centroid for 64
+// FMAs).  Per (point, centroid): 8 FMAs + 1 compare; the exact ANN-order distance is evaluated only for centroids whose
+// certified lower bound does not exceed the point's current best, so the result is the exact argmin (lowest index on
+// ties).
 template <int D>
 __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restrict__ frames,
                                                          const float *__restrict__ X,
                                                          const float *__restrict__ cen,  // [F][Kmax][D]
+                                                         const float *__restrict__ ch,   // [F][Kpad] (k_cen_h)
                                                          int *__restrict__ labels, float *__restrict__ dist,
-                                                         int Kmax) {
+                                                         int Kmax, int Kpad) {
     constexpr int P = GSC_ASSIGN_P, PP = P / 2;
     // dimensions of the bound: the second half of a feature row is the 1e-5-scaled cepstrum (enc:362); dropping
     // those non-negative terms keeps lb <= d and halves the FMA work
     constexpr int DF = (D >= 8) ? D / 2 : D;
-    __shared__ __align__(16) float s_c[GSC_ASSIGN_TILE * D];
-    __shared__ float s_h[GSC_ASSIGN_TILE];  // -0.5*|c|^2*(1-g), NaN-safe
+    constexpr int TILE = (D > 8) ? GSC_ASSIGN_TILE / 2 : GSC_ASSIGN_TILE;   // two buffers inside 48 KB of static shared memory
+    __shared__ __align__(128) float s_c[2][TILE * D];
+    __shared__ __align__(16) float s_h[2][TILE];  // -0.5*|c|^2*(1-g), NaN-safe
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const GscFrame f = frames[blockIdx.y];
     const int K = f.K;
     const long long base = (long long)blockIdx.x * blockDim.x * P;
     if (base >= f.N) return;
     const float *Xf = X + f.chunk_off * D;
     const float *cf = cen + (long long)f.slot * Kmax * D;
+    const float *hf = ch + (long long)f.slot * Kpad;
+    const int ntiles = (K + TILE - 1) / TILE;
+    auto request = [&](int t) {     // one thread: arm the buffer's barrier with the byte count, start both copies
+        const int k0 = t * TILE, kt = min(TILE, K - k0), buf = t & 1;
+        const unsigned bc = (unsigned)kt * D * 4u, bh = (unsigned)((kt + 3) & ~3) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's last readers (generic proxy) came first
+        gsc_mbar_expect_tx(&s_bar[buf], bc + bh);
+        gsc_bulk_g2s(s_c[buf], cf + (long long)k0 * D, bc, &s_bar[buf]);
+        gsc_bulk_g2s(s_h[buf], hf + k0, bh, &s_bar[buf]);
+    };
+    if (threadIdx.x == 0) {
+        gsc_mbar_init(&s_bar[0], 1); gsc_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && ntiles > 0) request(0);
     float x[P][D], thr[P], bd[P], hx[P];
     int bi[P];
 #pragma unroll
@@ -1716,32 +1782,26 @@ __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restr
     for (int q = 0; q < PP; ++q)
 #pragma unroll
         for (int k = 0; k < DF; ++k) xp[q][k] = gsc_a_pk2(x[2 * q][k], x[2 * q + 1][k]);
-    for (int k0 = 0; k0 < K; k0 += GSC_ASSIGN_TILE) {
-        const int kt = min(GSC_ASSIGN_TILE, K - k0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < kt * D; t += blockDim.x) s_c[t] = cf[(long long)k0 * D + t];
-        __syncthreads();
-        for (int t = threadIdx.x; t < kt; t += blockDim.x) {
-            float nc = 0.0f;
-#pragma unroll
-            for (int k = 0; k < DF; ++k) nc = fmaf(s_c[t * D + k], s_c[t * D + k], nc);
-            s_h[t] = -0.5f * nc * (1.0f - GSC_LB_GAMMA);
-        }
-        __syncthreads();
+    for (int t = 0; t < ntiles; ++t) {
+        const int k0 = t * TILE, kt = min(TILE, K - k0), buf = t & 1;
+        // the other buffer was released by the barrier that ended tile t-1: refill it while this tile is scored
+        if (threadIdx.x == 0 && t + 1 < ntiles) request(t + 1);
+        gsc_mbar_wait(&s_bar[buf], (unsigned)((t >> 1) & 1));
+        const float *sc = s_c[buf], *sh = s_h[buf];
 #pragma unroll 2
         for (int c = 0; c < kt; ++c) {
             float cc[DF];
             if (DF % 4 == 0) {
 #pragma unroll
                 for (int k = 0; k < DF / 4; ++k) {
-                    const float4 t4 = *reinterpret_cast<const float4 *>(&s_c[c * D + 4 * k]);
+                    const float4 t4 = *reinterpret_cast<const float4 *>(&sc[c * D + 4 * k]);
                     cc[4 * k] = t4.x; cc[4 * k + 1] = t4.y; cc[4 * k + 2] = t4.z; cc[4 * k + 3] = t4.w;
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < DF; ++k) cc[k] = s_c[c * D + k];
+                for (int k = 0; k < DF; ++k) cc[k] = sc[c * D + k];
             }
-            const float h = s_h[c];
+            const float h = sh[c];
             unsigned long long s2[PP];
 #pragma unroll
             for (int q = 0; q < PP; ++q) s2[q] = gsc_a_pk2(h, h);
@@ -1763,7 +1823,7 @@ __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restr
                     if (sv[p] >= thr[p]) {
                         float cr[D];
 #pragma unroll
-                        for (int k = 0; k < D; ++k) cr[k] = s_c[c * D + k];
+                        for (int k = 0; k < D; ++k) cr[k] = sc[c * D + k];
                         const float d = gsc_ann_dist<D>(x[p], cr);
                         if (d < bd[p]) {
                             bd[p] = d; bi[p] = k0 + c;
@@ -1773,6 +1833,7 @@ __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restr
                     }
             }
         }
+        __syncthreads();    // everybody is done with this buffer: it may be refilled (tile t+2)
     }
 #pragma unroll
     for (int p = 0; p < P; ++p) {

@@ -262,8 +262,8 @@ __device__ __forceinline__ float gsc_mkf(int e, int S) { return __uint_as_float(
 
 // T threads per CTA: every phase of a step is a latency chain (global loads, warp scans, a 256-long FADD chain), so
 // what keeps an SM busy is the number of independent frames resident on it, not the width of one CTA.
-template <int D, int T>
-__global__ void __launch_bounds__(T, 512 / T) k_seed2(const GscFrame *__restrict__ frames,
+template <int D, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_seed2(const GscFrame *__restrict__ frames,
                                                           const float *__restrict__ X,     // [sumN][D] original order
                                                           const float *__restrict__ Xs,    // [sumN][D] bucketed order
                                                           const float *__restrict__ pns,   // [sumN] norms, bucketed order
