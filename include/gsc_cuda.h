@@ -298,6 +298,19 @@ int gsc_debug_online_counters(gsc_ctx *ctx, unsigned long long *out, int n_frame
  * summaries + chain, number of steps; windows evaluated exactly, blocks visited, windows re-summarised, chain cycles. */
 int gsc_debug_seed_counters(gsc_ctx *ctx, unsigned long long *out, int n_frames);
 
+/* the frame planner's power scan and boundary selection (TEncoder.PrepareFrames enc:1374-1425, with
+ * the int16 -> Double staging of enc:1282-1285) on the device.  pcm planar [C][S], S already padded to the block size
+ * (enc:1319-1323); block = ChunkSize (under-sampling 1, blend 0).  starts[0..*n_frames) = first sample of every frame,
+ * exactly what the reference's sequential Double sums give (the sums are evaluated bit-exactly in parallel, see
+ * csrc/gsc_plan.cuh).  stats (optional, 4 values): windows added element by element in pass 1 / pass 2, boundary
+ * iterations (1 = every candidate was right), windows of pass 1. */
+int gsc_plan_frames(gsc_ctx *ctx, const int16_t *pcm, int64_t stride, int C, int64_t S, int sample_rate,
+                    double frame_length_ms, double vfr, int block, int64_t *starts, int max_frames, int *n_frames,
+                    uint64_t *stats);
+int gsc_plan_frames_dev(gsc_ctx *ctx, const int16_t *pcm_dev, int64_t stride, int C, int64_t S, int sample_rate,
+                        double frame_length_ms, double vfr, int block, int64_t *starts, int max_frames, int *n_frames,
+                        uint64_t *stats);
+
 /* The library's natural logarithm (csrc/gsc_log.h: correctly rounded, plain IEEE double operations; the cepstral
  * features enc:316-318 go through it) over a host array, so that a host can compare it value by value. */
 int gsc_log_array(gsc_ctx *ctx, const double *x, int64_t n, double *y);

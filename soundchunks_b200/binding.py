@@ -28,7 +28,7 @@ EXPORTS = [
     "gsc_assign", "gsc_split_begin", "gsc_split_step", "gsc_split_update", "gsc_split_end",
     "gsc_split_unique_id", "gsc_split_comm_init", "gsc_split_comm_destroy", "gsc_split_seed", "gsc_split_lloyd", "gsc_build_dictionary", "gsc_knnfit", "gsc_finalize_dictionary",
     "gsc_default_params", "gsc_dict_capacity", "gsc_encode_frames", "gsc_encode_frames_dev",
-    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_ctx_set_debug", "gsc_selftest_divider_division", "gsc_debug_online_counters", "gsc_debug_seed_counters",
+    "gsc_fetch_results", "gsc_fetch_stream", "gsc_fetch_quality", "gsc_fp32_peak_probe", "gsc_log_array", "gsc_plan_frames", "gsc_plan_frames_dev", "gsc_ctx_set_debug", "gsc_selftest_divider_division", "gsc_debug_online_counters", "gsc_debug_seed_counters",
 ]
 
 
@@ -215,6 +215,21 @@ class Context:
         out = np.zeros((n_frames, 8), np.uint64)
         self._ck(self.L.gsc_debug_seed_counters(C.c_void_p(self.h), _vp(out), n_frames))
         return out
+
+    def plan_frames(self, pcm, sample_rate, frame_length_ms=4000.0, vfr=1.0, block=4, max_frames=None, return_stats=False):
+        """enc:1374-1425 on the device: pcm planar int16 [C][S] (S padded to the block size) -> frame starts."""
+        pcm = _pcm(pcm)
+        Cn, S = pcm.shape
+        if max_frames is None:
+            max_frames = 4 * int(np.ceil(S / (sample_rate * frame_length_ms / 1000.0))) + 16
+        starts = np.zeros(max_frames, np.int64)
+        n = C.c_int(0)
+        st = (C.c_uint64 * 4)()
+        self._ck(self.L.gsc_plan_frames(C.c_void_p(self.h), _vp(pcm), C.c_int64(S), Cn, C.c_int64(S), sample_rate,
+                                        C.c_double(frame_length_ms), C.c_double(vfr), block, _vp(starts), max_frames, C.byref(n), st))
+        out = starts[:n.value].copy()
+        return (out, dict(exact_windows_pass1=int(st[0]), exact_windows_pass2=int(st[1]), boundary_iterations=int(st[2]),
+                          windows_pass1=int(st[3]))) if return_stats else out
 
     def log_array(self, x) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -435,3 +435,24 @@ def test_divider_kernel_forms_agree(ctx, oracle):
         assert d1 == d2 == d_ref and np.array_equal(v1, v_ref) and np.array_equal(v2, v_ref)
     v10 = ctx.find_attenuation_divider(_quiet(_audio(0.2, 44100, 1, 4)), 4, 10, return_v=True)   # other depth: plain division
     assert v10[0] == oracle.find_attenuation_divider(_quiet(_audio(0.2, 44100, 1, 4)), 4, 10)
+
+
+@pytest.mark.parametrize("channels,sr,seconds,fl,vfr,kind", [(1, 44100, 21.3, 4000.0, 1.0, "music"), (2, 48000, 12.0, 700.0, 1.0, "music"),
+                                                          (2, 44100, 9.0, 500.0, 0.5, "silence_lead"), (1, 32000, 6.5, 250.0, 1.0, "bursts"),
+                                                          (2, 44100, 3.1, 4000.0, 1.0, "short")])
+def test_frame_planner_on_device(ctx, oracle, channels, sr, seconds, fl, vfr, kind):
+    """gsc_plan_frames (power scan + boundary selection on the device, sequential Double sums
+    evaluated exactly in parallel) == oracle.plan_frames (enc:1374-1425), frame start by frame start."""
+    pcm = _audio(seconds, sr, channels, 41)
+    S = pcm.shape[1] // 4 * 4
+    pcm = np.ascontiguousarray(pcm[:, :S]).copy()
+    if kind == "silence_lead":
+        pcm[:, : int(2.2 * sr)] = 0                      # digital silence: the sums stay at +0 for 2.2 s
+    if kind == "bursts":
+        pcm[:, ::3] = (pcm[:, ::3].astype(np.int32) // 64).astype(np.int16)
+        pcm[:, int(1.0 * sr):int(1.5 * sr)] = 32767      # full-scale stretch: smp > avg, terms near (and just below) zero
+        pcm[:, int(3.0 * sr):int(3.2 * sr)] = -32768     # |x| > 1: slightly NEGATIVE terms
+    want = oracle.plan_frames(pcm, sr, frame_length_ms=fl, vfr=vfr)
+    got, st = ctx.plan_frames(pcm, sr, frame_length_ms=fl, vfr=vfr, return_stats=True)
+    assert np.array_equal(got, want), (got[:8], want[:8], st)
+    assert st["boundary_iterations"] <= 3 and st["exact_windows_pass1"] < st["windows_pass1"] // 4 + 64
