@@ -189,13 +189,9 @@ extern "C" int64_t gsch_padded_samples(int64_t S, const gsch_options *o) {
     return S <= 0 ? 0 : ((S - 1) / block + 1) * block;      // enc:1319
 }
 
-extern "C" int gsch_plan_frames(const int16_t *pcm, int64_t stride, int C, int64_t S, int sample_rate, gsch_options *o,
-                                int64_t *starts, int max_frames) {
-    if (!pcm || C <= 0 || S <= 0 || sample_rate <= 0 || !starts || max_frames <= 0) { fail("gsch_plan_frames: bad arguments"); return -1; }
-    if (check_options(o, sample_rate)) return -1;
+// enc:1325-1351: largest ChunksPerFrame whose projected size fits the bit rate (host scalar logic)
+static int solve_chunks_per_frame(gsch_options *o, int C, int64_t S, int sample_rate, int frameCount) {
     const int block = o->chunk_size - o->chunk_blend;
-    const int frameCount = (int)std::ceil((double)S / ((double)sample_rate * (o->frame_length_ms / 1000.0)));   // enc:1335
-    // enc:1325-1351: largest ChunksPerFrame whose projected size fits the bit rate
     {
         const double projected = o->bitrate > 0 ? std::ceil(((double)S / sample_rate) * ((double)o->bitrate * 1024.0 / 8.0)) : 2147483647.0;
         int cpf = o->chunks_per_frame + 1;
@@ -209,6 +205,16 @@ extern "C" int gsch_plan_frames(const int16_t *pcm, int64_t stride, int C, int64
         o->chunks_per_frame = cpf;
         if (cpf <= 0) { fail("Null ChunksPerFrame! (BitRate too low)"); return -1; }   // enc:1360
     }
+    return 0;
+}
+
+extern "C" int gsch_plan_frames(const int16_t *pcm, int64_t stride, int C, int64_t S, int sample_rate, gsch_options *o,
+                                int64_t *starts, int max_frames) {
+    if (!pcm || C <= 0 || S <= 0 || sample_rate <= 0 || !starts || max_frames <= 0) { fail("gsch_plan_frames: bad arguments"); return -1; }
+    if (check_options(o, sample_rate)) return -1;
+    const int block = o->chunk_size - o->chunk_blend;
+    const int frameCount = (int)std::ceil((double)S / ((double)sample_rate * (o->frame_length_ms / 1000.0)));   // enc:1335
+    if (solve_chunks_per_frame(o, C, S, sample_rate, frameCount)) return -1;
     auto rms_at = [&](int64_t i) {
         double smp = 0.0;
         for (int j = 0; j < C; ++j) { const double x = float_sample(pcm[(size_t)j * stride + i]); smp += x * x; }
@@ -427,8 +433,20 @@ extern "C" int gsch_encode_pcm(const int16_t *pcm_in, int64_t stride_in, int C, 
     const int64_t S = gsch_padded_samples(S0, &o);
     std::vector<int16_t> pcm((size_t)C * S, 0);
     for (int j = 0; j < C; ++j) memcpy(&pcm[(size_t)j * S], pcm_in + (size_t)j * stride_in, sizeof(int16_t) * (size_t)S0);
-    std::vector<int64_t> starts((size_t)(S / cs + 2));
-    const int F = gsch_plan_frames(pcm.data(), S, C, S, sample_rate, &o, starts.data(), (int)starts.size());
+    // PrepareFrames (enc:1294-1429): the ChunksPerFrame solver is host scalar logic; the power scan and the boundary
+    // selection over all samples run on the device (gsc_plan_frames, bit-exact; gsch_plan_frames is the host form)
+    const int frameCount = (int)std::ceil((double)S / ((double)sample_rate * (o.frame_length_ms / 1000.0)));   // enc:1335
+    if (solve_chunks_per_frame(&o, C, S, sample_rate, frameCount)) return 1;
+    std::vector<int64_t> starts((size_t)frameCount * 4 + 16);
+    int F = 0;
+    {
+        gsc_ctx *pctx = gsc_create(0);
+        if (!pctx) return fail("no usable sm_100 CUDA device: %s", gsc_last_error());
+        const int rc = gsc_plan_frames(pctx, pcm.data(), S, C, S, sample_rate, o.frame_length_ms, o.vfr, cs - o.chunk_blend,
+                                       starts.data(), (int)starts.size(), &F, nullptr);
+        if (rc != GSC_OK) { fail("gsc_plan_frames: %s", gsc_last_error()); gsc_destroy(pctx); return 1; }
+        gsc_destroy(pctx);
+    }
     if (F <= 0) return 1;
     starts.resize(F);
     std::vector<int> fsamples(F);
