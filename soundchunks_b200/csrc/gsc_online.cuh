@@ -906,21 +906,25 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
 // shuffles; labels are written back coalesced per tile; lane 0 carries the Double error sum in point order.
 // grid = ceil(F / GSC_OW_WARPS), block = 32 * GSC_OW_WARPS.
 // ---------------------------------------------------------------------------
-#define GSC_OW_WARPS 2
-#define GSC_OW_CPL 8          // centroids per lane
+#define GSC_OW_CPL 8          // centroids per lane with one warp per frame (K <= 256)
 
-template <int D>
-__global__ void __maxnreg__(184) k_online_warp(const GscFrame *__restrict__ frames, int F,
-                                                                   const float *__restrict__ X,    // [sumN][D]
-                                                                   float *__restrict__ cen,        // [F][Kmax][D] in/out
-                                                                   int *__restrict__ labels,       // [sumN] out
-                                                                   int *__restrict__ passes_out,   // [F]
-                                                                   double *__restrict__ err_out,   // [F]
-                                                                   double tol, int max_passes, int Kmax) {
+// WPF warps per frame (1 or 2): with two, each warp owns half of the codebook (4 rows per lane), the two warps' best
+// keys meet in shared memory (double-buffered by point parity: one 64-thread barrier per point) and the SM holds twice
+// as many warps for the same number of frames -- the frame count is the only parallelism of this path.
+template <int D, int WPF>
+__global__ void __launch_bounds__(32 * WPF, WPF == 1 ? 10 : 8) k_online_warp(const GscFrame *__restrict__ frames, int F,
+                                                                  const float *__restrict__ X,    // [sumN][D]
+                                                                  float *__restrict__ cen,        // [F][Kmax][D] in/out
+                                                                  int *__restrict__ labels,       // [sumN] out
+                                                                  int *__restrict__ passes_out,   // [F]
+                                                                  double *__restrict__ err_out,   // [F]
+                                                                  double tol, int max_passes, int Kmax) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int CPL = GSC_OW_CPL;
-    const int lane = threadIdx.x & 31;
-    const int fi = blockIdx.x * GSC_OW_WARPS + (threadIdx.x >> 5);
+    constexpr int CPL = GSC_OW_CPL / WPF;
+    __shared__ unsigned long long s_key[2][2];
+    __shared__ int s_stop;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fi = blockIdx.x;
     if (fi >= F) return;
     const GscFrame f = frames[fi];
     const int K = f.K, N = f.N;
@@ -933,18 +937,19 @@ __global__ void __maxnreg__(184) k_online_warp(const GscFrame *__restrict__ fram
     int cnt[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-        const int ci = lane + 32 * j;
+        const int ci = warp * (32 * CPL) + lane + 32 * j;
 #pragma unroll
         for (int k = 0; k < D; ++k) c[j][k] = (ci < K) ? cf[(long long)ci * D + k] : __int_as_float(0x7fc00000);   // dead rows never win
         cnt[j] = 1;                                                                                                 // enc:717-721
     }
-    double err = 3.40282346638528860e+38;   // enc:724 (all lanes carry the same value)
+    double err = 3.40282346638528860e+38;   // enc:724 (every thread carries the same value)
     int iter = 0;
     for (;;) {
         const double prevErr = err;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) { rate[j] = gsc_rate(cnt[j]); cnt[j] = 1; }   // enc:735 (cnt_prev is constant during a pass), 754-758
         double e_run = 0.0;
+        int par = 0;
         for (int base = 0; base < N; base += 32) {
             const int tn = min(32, N - base);
             float xt[D];
@@ -952,7 +957,7 @@ __global__ void __maxnreg__(184) k_online_warp(const GscFrame *__restrict__ fram
             for (int k = 0; k < D; ++k) xt[k] = 0.0f;
             if (lane < tn) gsc_load_row<D>(Xf, base + lane, xt);
             int mylab = 0;
-            for (int p = 0; p < tn; ++p) {
+            for (int p = 0; p < tn; ++p, par ^= 1) {
                 float x[D];
 #pragma unroll
                 for (int k = 0; k < D; ++k) x[k] = __shfl_sync(FULL, xt[k], p);
@@ -965,15 +970,22 @@ __global__ void __maxnreg__(184) k_online_warp(const GscFrame *__restrict__ fram
                     if (d < bd) { bd = d; bj = j; }
                 }
                 const unsigned dk = (bj >= 0) ? __float_as_uint(bd) : 0xffffffffu;      // distances are >= 0: bits order them
-                const unsigned m = __reduce_min_sync(FULL, dk);
-                const unsigned ci = __reduce_min_sync(FULL, (dk == m && bj >= 0) ? (unsigned)(lane + 32 * bj) : 0xffffffffu);
+                unsigned m = __reduce_min_sync(FULL, dk);
+                unsigned ci = __reduce_min_sync(FULL, (dk == m && bj >= 0) ? (unsigned)(warp * (32 * CPL) + lane + 32 * bj) : 0xffffffffu);
+                if (WPF == 2) {
+                    if (lane == 0) s_key[par][warp] = ((unsigned long long)m << 32) | ci;
+                    __syncthreads();
+                    const unsigned long long o = s_key[par][warp ^ 1], mine = ((unsigned long long)m << 32) | ci;
+                    const unsigned long long w2 = o < mine ? o : mine;
+                    m = (unsigned)(w2 >> 32); ci = (unsigned)(w2 & 0xffffffffu);
+                }
                 int win = (int)ci;
                 float dw = __uint_as_float(m);
                 if (ci == 0xffffffffu) { win = 0; dw = INFINITY; }                       // every row NaN: centroid 0, d = +inf
-                if (lane == (win & 31)) {
+                if (warp == win / (32 * CPL) && lane == (win & 31)) {
                     // enc:735-740, 744 on the winning row (static register indices: one case per owned row)
-                    switch (win >> 5) {
-#define GSC_OW_CASE(J) case J: { _Pragma("unroll") for (int k = 0; k < D; ++k) { const float v = x[k] - c[J][k]; const float mm = v * rate[J]; c[J][k] = c[J][k] + mm; } cnt[J] += 1; } break;
+                    switch ((win % (32 * CPL)) >> 5) {
+#define GSC_OW_CASE(J) case J: if (J < CPL) { _Pragma("unroll") for (int k = 0; k < D; ++k) { const float v = x[k] - c[J < CPL ? J : 0][k]; const float mm = v * rate[J < CPL ? J : 0]; c[J < CPL ? J : 0][k] = c[J < CPL ? J : 0][k] + mm; } cnt[J < CPL ? J : 0] += 1; } break;
                         GSC_OW_CASE(0) GSC_OW_CASE(1) GSC_OW_CASE(2) GSC_OW_CASE(3)
                         GSC_OW_CASE(4) GSC_OW_CASE(5) GSC_OW_CASE(6) GSC_OW_CASE(7)
 #undef GSC_OW_CASE
@@ -981,9 +993,9 @@ __global__ void __maxnreg__(184) k_online_warp(const GscFrame *__restrict__ fram
                     }
                 }
                 if (lane == p) mylab = win;                                             // enc:742
-                e_run += (double)sqrtf(dw / (float)D);                                  // enc:743 (same value in every lane)
+                e_run += (double)sqrtf(dw / (float)D);                                  // enc:743 (same value in every thread)
             }
-            if (lane < tn) lab[base + lane] = mylab;
+            if (warp == 0 && lane < tn) lab[base + lane] = mylab;
         }
         err = e_run;
         ++iter;
@@ -992,11 +1004,12 @@ __global__ void __maxnreg__(184) k_online_warp(const GscFrame *__restrict__ fram
     }
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-        const int ci = lane + 32 * j;
+        const int ci = warp * (32 * CPL) + lane + 32 * j;
         if (ci < K) {
 #pragma unroll
             for (int k = 0; k < D; ++k) cf[(long long)ci * D + k] = c[j][k];
         }
     }
-    if (lane == 0) { passes_out[f.slot] = iter; err_out[f.slot] = err; }
+    if (threadIdx.x == 0) { passes_out[f.slot] = iter; err_out[f.slot] = err; }
+    (void)s_stop;
 }
