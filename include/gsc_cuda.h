@@ -148,8 +148,10 @@ int gsc_knn_scan_reduce(gsc_ctx *ctx, const float *X, int N, int D,
 
 /* Plain batch Lloyd (BASELINE.json's 1e-4 centroid contract): `iters` x
  * (exact assign, mean), then a final assign.  centroids in/out.  Member rows
- * are accumulated in Double and the mean is rounded to Single once, so the
- * result does not depend on the summation order (see gsc_split_*). */
+ * are accumulated in Double and the mean is rounded to Single once: two
+ * summation orders give the same Single unless the Double sums straddle a
+ * rounding boundary of the Single (about 1e-9 per coordinate), which is why the
+ * split over GPUs (gsc_split_*) reproduces the single-GPU centroids. */
 int gsc_lloyd(gsc_ctx *ctx, const float *X, int N, int D, float *centroids,
               int K, int iters, int32_t *labels);
 

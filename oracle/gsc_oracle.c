@@ -3,6 +3,9 @@
  *
  * TEST INFRASTRUCTURE ONLY (see gsc_oracle.h).  PARITY UNPINNED: there are no
  * reference golden vectors for this path and the reference cannot run here.
+ * Third-party algorithms restated from their published sources because the
+ * reference ships them as binaries only: yakmo (N. Yoshinaga; GliGli's DLL fork,
+ * yakmo_single.dll, no version pin) and ANN 1.1.2 (D. Mount, S. Arya; ANN.dll).
  *
  * Citations:  enc:L = /root/reference/encoder/encoder.lpr line L
  *             dec:L = /root/reference/decoder/decoder.lpr line L
@@ -1178,9 +1181,7 @@ int gsc_ref_encode_frame(const int16_t *pcm, int64_t stride, int C, int S,
     int32_t *band = (int32_t *)malloc(sizeof(int32_t) * N);
     if (p->kmeans_mode == 3 && !p->band_all) {
         gsc_ref_knnfit_kdtree(dict, datten, R, cs, bits, divider, raw, N, best, use);
-        int32_t *b2 = (int32_t *)malloc(sizeof(int32_t) * N);
-        for (int j = 0; j < N; ++j) band[j] = 0;
-        free(b2);
+        for (int j = 0; j < N; ++j) band[j] = 0;       /* (band populations are not computed in this mode) */
     } else if (p->band_all) {
         int32_t *b64 = (int32_t *)malloc(sizeof(int32_t) * N);
         gsc_ref_knnfit(dict, datten, R, cs, bits, divider, raw, N, b64, NULL, band, best, NULL);
