@@ -422,14 +422,19 @@ class Context:
         return out
 
     def fetch_stream(self, n_frames: int, sample_rate: int):
-        """.gsc bytes of the last batch, packed on the device -> (bytes, per-frame sizes)."""
+        """.gsc bytes of the last batch, packed on the device -> (bytearray, per-frame sizes)."""
         sizes = np.zeros(n_frames, np.int64)
         total = C.c_int64(0)
         # sizing call: packs on the device and brings back 8 bytes per frame; the second call copies the bytes (once)
         self._ck(self.L.gsc_fetch_stream(C.c_void_p(self.h), n_frames, sample_rate, None, C.c_int64(0), _vp(sizes), C.byref(total)))
-        out = np.empty(max(total.value, 1), np.uint8)
-        self._ck(self.L.gsc_fetch_stream(C.c_void_p(self.h), n_frames, sample_rate, _vp(out), C.c_int64(total.value), _vp(sizes), C.byref(total)))
-        return out[:total.value].tobytes(), sizes
+        out = bytearray(max(total.value, 1))        # the library writes straight into it: no second host copy
+        buf = (C.c_char * len(out)).from_buffer(out)
+        self._ck(self.L.gsc_fetch_stream(C.c_void_p(self.h), n_frames, sample_rate, C.cast(buf, C.c_void_p), C.c_int64(total.value),
+                                         _vp(sizes), C.byref(total)))
+        del buf
+        if total.value != len(out):
+            del out[total.value:]
+        return out, sizes
 
     def fetch_quality(self, n_frames: int):
         """-> (sum of squared int16 errors per frame, samples per frame); PsyADelta = sqrt(sum / sum)."""

@@ -489,9 +489,23 @@ static int stage_assign(gsc_ctx *c, int D, bool want_dist) {
     TRY(c->cenh.ensure(4 * (size_t)c->F * Kpad));
     dim3 gh((Kpad + 255) / 256, c->F);
     DISPATCH_D(D, LAUNCH(c, k_cen_h<D>, gh, 256, 0, c->frames.as<GscFrame>(), c->cen.as<float>(), c->cenh.as<float>(), c->Kmax, Kpad));
-    dim3 grid((c->maxN + GSC_ASSIGN_T * GSC_ASSIGN_P - 1) / (GSC_ASSIGN_T * GSC_ASSIGN_P), c->F);
-    DISPATCH_D(D, LAUNCH(c, k_assign<D>, grid, GSC_ASSIGN_T, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->cen.as<float>(),
-                         c->cenh.as<float>(), c->labels.as<int>(), want_dist ? c->dist.as<float>() : nullptr, c->Kmax, Kpad));
+    // points per thread: 8 for batches (fewest codebook-tile reads per FMA); 4 or 2 when that would leave SMs without
+    // work (a shard of an oversized frame split over many GPUs: 131,072 points are only 128 CTAs at 8)
+    const char *pe = getenv("GSC_ASSIGN_PTS");          // measurement / test override, read per call
+    const int forced = pe ? atoi(pe) : 0;
+    auto ctas = [&](int P) { return ((long long)c->maxN + GSC_ASSIGN_T * P - 1) / (GSC_ASSIGN_T * P) * c->F; };
+    int P = 8;
+    while (P > 2 && ctas(P) < 2 * 148) P >>= 1;
+    if (forced == 8 || forced == 4 || forced == 2) P = forced;
+#define GSC_ASSIGN_LAUNCH(PV)                                                                                                     \
+    {                                                                                                                             \
+        dim3 grid((unsigned)(ctas(PV) / c->F), c->F);                                                                             \
+        DISPATCH_D(D, LAUNCH(c, (k_assign<D, PV>), grid, GSC_ASSIGN_T, 0, c->frames.as<GscFrame>(), c->feat.as<float>(),          \
+                             c->cen.as<float>(), c->cenh.as<float>(), c->labels.as<int>(),                                        \
+                             want_dist ? c->dist.as<float>() : nullptr, c->Kmax, Kpad));                                          \
+    }
+    if (P == 8) GSC_ASSIGN_LAUNCH(8) else if (P == 4) GSC_ASSIGN_LAUNCH(4) else GSC_ASSIGN_LAUNCH(2)
+#undef GSC_ASSIGN_LAUNCH
     return GSC_OK;
 }
 

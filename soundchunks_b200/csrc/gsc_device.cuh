@@ -92,15 +92,35 @@ __device__ __forceinline__ void gsc_chunk_attrs(const double (&x)[CS], const Gsc
     rev = p1 > p2;
 }
 
-// ANN distance (float, left to right, separate multiply and add).
+// ANN distance (float, left to right, separate multiply and add): d = 0; for k: t = q_k - p_k; d = d + t*t.
+// The subtractions and the squarings of two neighbouring dimensions are independent IEEE operations, so they go through
+// the packed FP32 pipe (sub.rn.f32x2 / mul.rn.f32x2 -> FADD2 / FMUL2: two results per issue slot, bit for bit the scalar
+// results); the accumulation stays a chain of scalar adds in the reference's order.  (Not add.rn.f32x2: ptxas 12.9
+// contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with explicit .rn and -fmad=false, which would round once
+// instead of twice; a packed multiply followed by scalar adds is left alone -- checked in the SASS.)
+__device__ __forceinline__ unsigned long long gsc_pk2f(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void gsc_upk2f(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 template <int D>
 __device__ __forceinline__ float gsc_ann_dist(const float (&q)[D], const float (&p)[D]) {
     float d = 0.0f;
+    if (D % 2 == 0) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        float t = q[k] - p[k];
-        float m = t * t;
-        d = d + m;
+        for (int k = 0; k < D / 2; ++k) {
+            unsigned long long t, m;
+            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(gsc_pk2f(q[2 * k], q[2 * k + 1])), "l"(gsc_pk2f(p[2 * k], p[2 * k + 1])));
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(t), "l"(t));
+            float m0, m1;
+            gsc_upk2f(m, m0, m1);
+            d = d + m0;
+            d = d + m1;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float t = q[k] - p[k];
+            float m = t * t;
+            d = d + m;
+        }
     }
     return d;
 }

@@ -1722,14 +1722,16 @@ __global__ void k_cen_h(const GscFrame *__restrict__ frames, const float *__rest
 // FMAs).  Per (point, centroid): 8 FMAs + 1 compare; the exact ANN-order distance is evaluated only for centroids whose
 // certified lower bound does not exceed the point's current best, so the result is the exact argmin (lowest index on
 // ties).
-template <int D>
+// P points per thread: 8 for batches (fewest tile reads per FMA), 2 when a launch would otherwise have fewer CTAs than
+// the SMs can hold (one oversized frame split over many GPUs: a shard of 131,072 points is 128 CTAs at P = 8).
+template <int D, int P>
 __global__ void __launch_bounds__(GSC_ASSIGN_T) k_assign(const GscFrame *__restrict__ frames,
                                                          const float *__restrict__ X,
                                                          const float *__restrict__ cen,  // [F][Kmax][D]
                                                          const float *__restrict__ ch,   // [F][Kpad] (k_cen_h)
                                                          int *__restrict__ labels, float *__restrict__ dist,
                                                          int Kmax, int Kpad) {
-    constexpr int P = GSC_ASSIGN_P, PP = P / 2;
+    constexpr int PP = P / 2;
     // dimensions of the bound: the second half of a feature row is the 1e-5-scaled cepstrum (enc:362); dropping
     // those non-negative terms keeps lb <= d and halves the FMA work
     constexpr int DF = (D >= 8) ? D / 2 : D;

@@ -192,6 +192,19 @@ def test_lloyd(ctx, oracle, K, iters):
     assert np.mean(l_gpu != l_ref) < 1e-3
 
 
+@pytest.mark.parametrize("pts", [2, 4, 8])
+def test_assign_points_per_thread_variants(ctx, oracle, pts, monkeypatch):
+    """k_assign<D, P>: the three points-per-thread instantiations (chosen by launch size) give the oracle's labels and
+    distances bit for bit."""
+    pcm, raw, attr, feat = _features(oracle, 0.3)
+    c0, _, _ = oracle.yakmo(feat, 1000)
+    l_ref, d_ref = oracle.assign(feat, c0)
+    monkeypatch.setenv("GSC_ASSIGN_PTS", str(pts))
+    l_gpu, d_gpu = ctx.assign(feat, c0)
+    assert np.array_equal(l_gpu, l_ref)
+    assert np.array_equal(d_gpu.view(np.uint32), d_ref.view(np.uint32))
+
+
 def test_assign_exact(ctx, oracle):
     pcm, raw, attr, feat = _features(oracle, 0.4)
     c0, _, _ = oracle.yakmo(feat, 777)
@@ -456,3 +469,23 @@ def test_frame_planner_on_device(ctx, oracle, channels, sr, seconds, fl, vfr, ki
     got, st = ctx.plan_frames(pcm, sr, frame_length_ms=fl, vfr=vfr, return_stats=True)
     assert np.array_equal(got, want), (got[:8], want[:8], st)
     assert st["boundary_iterations"] <= 3 and st["exact_windows_pass1"] < st["windows_pass1"] // 4 + 64
+
+
+def test_other_chunk_sizes(ctx, oracle):
+    """-cs 2 (features of dimension 4) runs the same path bit for bit; -cs 8 (dimension 16) is refused loudly by the
+    online k-means (its register tile is built for D <= 8) but runs in Lloyd mode."""
+    import soundchunks_b200 as sc
+    pcm = _quiet(_audio(0.25, 44100, 2, 61))
+    r = ctx.encode_frames([pcm], chunk_size=2, chunk_bit_depth=12, chunks_per_frame=512)[0]
+    blob, _ = ctx.fetch_stream(1, 44100)
+    ref = oracle.encode_frame(pcm, chunk_size=2, chunk_bit_depth=12, chunks_per_frame=512, band_all=1)
+    assert (r.N, r.R, r.divider, r.passes, r.err) == (ref.N, ref.R, ref.divider, ref.passes, ref.err)
+    assert blob == oracle.write_frame(ref, 2, 2, 12, 44100)
+    with pytest.raises(sc.GscError):
+        ctx.encode_frames([pcm], chunk_size=8, chunk_bit_depth=12, chunks_per_frame=256)
+    r8 = ctx.encode_frames([pcm], chunk_size=8, chunk_bit_depth=12, chunks_per_frame=256, kmeans_mode=1, lloyd_iters=3)[0]
+    ref8 = oracle.encode_frame(pcm, chunk_size=8, chunk_bit_depth=12, chunks_per_frame=256, kmeans_mode=1, lloyd_iters=3, band_all=1)
+    assert (r8.N, r8.divider) == (ref8.N, ref8.divider)
+    dec_g, _ = oracle.decode(oracle.write_frame(oracle.FrameResult(r8.N, r8.R, r8.divider, 0, 0.0, r8.dict, r8.datten, r8.index, r8.attr, r8.overfull), 2, 8, 12, 44100))
+    dec_r, _ = oracle.decode(oracle.write_frame(ref8, 2, 8, 12, 44100))
+    assert abs(oracle.snr_db(pcm, dec_g) - oracle.snr_db(pcm, dec_r)) < 0.05

@@ -4,7 +4,10 @@ over the ranks; the collective (ncclAllReduce of the K x 9 Double partial sums) 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/split_frame.py [--points 1048576] [--iters 10] [--check]
 torch.distributed is only the transport of the 128-byte NCCL id and of the max-over-ranks of the times.
---check compares with the single-GPU gsc_lloyd of the whole frame (bit-identical by construction)."""
+--check compares with the single-GPU gsc_lloyd of the whole frame: BASELINE.json's 1e-4 relative is asserted; bit
+identity is reported.  (The partial sums are Doubles of float terms and almost always exact, so the order of the
+additions -- atomics on one GPU, NCCL's reduction tree over ranks -- rarely shows: 2 and 4 ranks came out bit
+identical, 8 ranks differed in 2 of 32,768 coordinates by one float ulp with every label equal.)"""
 import argparse
 import json
 import os
@@ -43,7 +46,16 @@ def run_split(ctx, rank, world, points, K, iters, bcast, maxred, check=False, se
         ref_cen, ref_lab = ctx.lloyd(full, c0, iters)
         out["bit_identical_to_single_gpu"] = bool(np.array_equal(cen.view(np.uint32), ref_cen.view(np.uint32))
                                                   and np.array_equal(labels, ref_lab[lo:hi]))
-        assert out["bit_identical_to_single_gpu"], out
+        rel = np.max(np.abs(cen - ref_cen), axis=1) / np.maximum(np.max(np.abs(ref_cen), axis=1), 1e-12)
+        out["check"] = {"centroid_coords_differing": int((cen.view(np.uint32) != ref_cen.view(np.uint32)).sum()),
+                        "centroid_max_rel_diff": float(rel.max()), "labels_differing": int((labels != ref_lab[lo:hi]).sum()),
+                        "rank": rank}
+        if not out["bit_identical_to_single_gpu"]:      # one iteration at a time: where does it start?
+            for it in (1, 2, 3):
+                c_s, _, _ = ctx.split_lloyd(feat, c0, it)
+                c_r, _ = ctx.lloyd(full, c0, it)
+                out["check"][f"coords_differing_after_{it}"] = int((c_s.view(np.uint32) != c_r.view(np.uint32)).sum())
+        assert rel.max() <= 1e-4, out                   # BASELINE.json's contract; bit-identity is reported
     if world > 1:
         ctx.split_comm_destroy()
     return out
