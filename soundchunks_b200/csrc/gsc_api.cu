@@ -605,10 +605,11 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     // compile without register spills are used (build.py checks).
     // K <= 256: one warp per frame, the codebook in registers, the rule run literally (k_online_warp)
     if (K <= 32 * GSC_OW_CPL && !(c->debug & GSC_DBG_ONLINE_BATCHED) && (D == 8 || D == 4)) {
-        static const int wpf = [] { const char *e = getenv("GSC_OW_WARPS"); return (e && atoi(e) == 1) ? 1 : 2; }();
+        const char *we = getenv("GSC_OW_WARPS");                  // warps per frame: 1 (default), 2 = the codebook split over two warps
+        const int wpf = (we && atoi(we) == 2) ? 2 : 1;
 #define GSC_OW_LAUNCH(DD, WW)                                                                                        \
         LAUNCH(c, (k_online_warp<DD, WW>), c->F, 32 * WW, 0, c->frames.as<GscFrame>(), c->F, c->feat.as<float>(),    \
-               c->cen.as<float>(), c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax)
+               c->cen.as<float>(), c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, 1.0f)
         if (D == 8) { if (wpf == 1) GSC_OW_LAUNCH(8, 1); else GSC_OW_LAUNCH(8, 2); }
         else { if (wpf == 1) GSC_OW_LAUNCH(4, 1); else GSC_OW_LAUNCH(4, 2); }
 #undef GSC_OW_LAUNCH

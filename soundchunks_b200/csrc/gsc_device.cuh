@@ -111,7 +111,7 @@ __device__ __forceinline__ float gsc_ann_dist(const float (&q)[D], const float (
             asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(t), "l"(t));
             float m0, m1;
             gsc_upk2f(m, m0, m1);
-            d = d + m0;
+            d = (k == 0) ? m0 : d + m0;      // 0 + m0 == m0 bit for bit: a square is +0, positive or NaN, never -0
             d = d + m1;
         }
     } else {
@@ -123,6 +123,27 @@ __device__ __forceinline__ float gsc_ann_dist(const float (&q)[D], const float (
         }
     }
     return d;
+}
+
+// The same distance for TWO codebook rows at once: p2[k] holds (row A's k-th coordinate, row B's) as a packed pair, so the
+// subtraction, the squaring AND the ordered accumulation of both rows go through the packed pipe: 3 instructions per
+// dimension for two rows.  The accumulation d = d + m is issued as fma(m, 1, d): the product m * 1 is exact, so the one
+// rounding of the fma is the rounding of the addition, bit for bit.  `ones` must be (1.0f, 1.0f) read at RUN time (a
+// kernel parameter): with a literal 1 ptxas rewrites fma(m,1,d) to an add and then contracts the preceding multiply
+// into it (FFMA2 of t*t+d: one rounding where the reference has two) -- seen in the SASS, hence the detour.
+template <int D>
+__device__ __forceinline__ void gsc_ann_dist2(const float (&q)[D], const unsigned long long (&p2)[D], unsigned long long ones,
+                                              float &dA, float &dB) {
+    unsigned long long d2 = 0ull;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        unsigned long long t, m;
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(gsc_pk2f(q[k], q[k])), "l"(p2[k]));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(t), "l"(t));
+        if (k == 0) d2 = m;                   // 0 + m == m: a square is +0, positive or NaN
+        else asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d2) : "l"(m), "l"(ones), "l"(d2));
+    }
+    gsc_upk2f(d2, dA, dB);
 }
 
 // yakmo distance (init() RVA 0x1dca): d = (cn + pn) + 0; d -= (p_k + p_k) * c_k

@@ -902,11 +902,49 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
 // order (ANN: sum (x-c)^2 left to right, no FMA), two redux steps give the nearest centroid with the lowest index on
 // ties, the owning lane moves its row.  The per-batch machinery of k_online (filter, lists, resolver rounds, three
 // block barriers per batch) costs more than scoring 256 centroids outright; here the warps of an SM are independent
-// frames and keep its issue slots busy.  Points are fetched 32 at a time (one row per lane) and broadcast by
-// shuffles; labels are written back coalesced per tile; lane 0 carries the Double error sum in point order.
+// frames and keep its issue slots busy.  Every lane reads the point itself (one broadcast load, issued a whole point
+// ahead of its use); labels are written back coalesced per tile of 32 points; the Double error sum is taken in point
+// order by warp 0, one tile behind (see the pass loop).
 // grid = ceil(F / GSC_OW_WARPS), block = 32 * GSC_OW_WARPS.
 // ---------------------------------------------------------------------------
 #define GSC_OW_CPL 8          // centroids per lane with one warp per frame (K <= 256)
+
+// enc:735-740, 744 on one codebook row: v = x - c; m = v * rate; c = c + m.  Subtractions and products in pairs through the
+// packed FP32 pipe (bit for bit the scalar results), the final additions scalar (see gsc_ann_dist on why not packed).
+template <int D>
+__device__ __forceinline__ void gsc_ow_update(float (&c)[D], const float (&x)[D], float rate) {
+    if (D % 2 == 0) {
+        const unsigned long long r2 = gsc_pk2f(rate, rate);
+#pragma unroll
+        for (int k = 0; k < D / 2; ++k) {
+            unsigned long long t, m;
+            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(gsc_pk2f(x[2 * k], x[2 * k + 1])), "l"(gsc_pk2f(c[2 * k], c[2 * k + 1])));
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(t), "l"(r2));
+            float m0, m1;
+            gsc_upk2f(m, m0, m1);
+            c[2 * k] = c[2 * k] + m0;
+            c[2 * k + 1] = c[2 * k + 1] + m1;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) { const float v = x[k] - c[k]; const float mm = v * rate; c[k] = c[k] + mm; }
+    }
+}
+
+// the same on row H (0 or 1) of a packed pair of rows
+template <int D, int H>
+__device__ __forceinline__ void gsc_ow_update2(unsigned long long (&c2)[D], const float (&x)[D], float rate) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        float a, b;
+        gsc_upk2f(c2[k], a, b);
+        const float cur = H ? b : a;
+        const float v = x[k] - cur;
+        const float mm = v * rate;
+        const float nw = cur + mm;
+        c2[k] = H ? gsc_pk2f(a, nw) : gsc_pk2f(nw, b);
+    }
+}
 
 // WPF warps per frame (1 or 2): with two, each warp owns half of the codebook (4 rows per lane), the two warps' best
 // keys meet in shared memory (double-buffered by point parity: one 64-thread barrier per point) and the SM holds twice
@@ -918,12 +956,17 @@ __global__ void __launch_bounds__(32 * WPF, WPF == 1 ? 10 : 8) k_online_warp(con
                                                                   int *__restrict__ labels,       // [sumN] out
                                                                   int *__restrict__ passes_out,   // [F]
                                                                   double *__restrict__ err_out,   // [F]
-                                                                  double tol, int max_passes, int Kmax) {
+                                                                  double tol, int max_passes, int Kmax,
+                                                                  float one) {                    // 1.0f (see gsc_ann_dist2)
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int CPL = GSC_OW_CPL / WPF;
+    static_assert(CPL % 2 == 0, "rows are held in pairs");
     __shared__ unsigned long long s_key[2][2];
     __shared__ int s_stop;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned sk_mine = (unsigned)__cvta_generic_to_shared(&s_key[0][warp & 1]);
+    unsigned sk_other = (unsigned)__cvta_generic_to_shared(&s_key[0][(warp & 1) ^ 1]);
+    asm volatile("" : "+r"(sk_mine), "+r"(sk_other));      // computed once: not to be rematerialised (S2R) in the point loop
     const int fi = blockIdx.x;
     if (fi >= F) return;
     const GscFrame f = frames[fi];
@@ -933,83 +976,148 @@ __global__ void __launch_bounds__(32 * WPF, WPF == 1 ? 10 : 8) k_online_warp(con
     int *lab = labels + f.chunk_off;
     float *cf = cen + (long long)f.slot * Kmax * D;
 
-    float c[CPL][D], rate[CPL];
+    // rows 2q and 2q+1 of this lane as packed pairs per coordinate (gsc_ann_dist2)
+    unsigned long long c2[CPL / 2][D];
+    float rate[CPL];
     int cnt[CPL];
+    const unsigned long long ones = gsc_pk2f(one, one);
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-        const int ci = warp * (32 * CPL) + lane + 32 * j;
+    for (int q = 0; q < CPL / 2; ++q) {
+        const int ca = warp * (32 * CPL) + lane + 32 * (2 * q), cb = ca + 32;
 #pragma unroll
-        for (int k = 0; k < D; ++k) c[j][k] = (ci < K) ? cf[(long long)ci * D + k] : __int_as_float(0x7fc00000);   // dead rows never win
-        cnt[j] = 1;                                                                                                 // enc:717-721
+        for (int k = 0; k < D; ++k)                                                                   // dead rows (NaN) never win
+            c2[q][k] = gsc_pk2f((ca < K) ? cf[(long long)ca * D + k] : __int_as_float(0x7fc00000),
+                                (cb < K) ? cf[(long long)cb * D + k] : __int_as_float(0x7fc00000));
+        cnt[2 * q] = 1; cnt[2 * q + 1] = 1;                                                           // enc:717-721
     }
-    double err = 3.40282346638528860e+38;   // enc:724 (every thread carries the same value)
+    double err = 3.40282346638528860e+38;   // enc:724 (warp 0 carries it)
     int iter = 0;
     for (;;) {
         const double prevErr = err;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) { rate[j] = gsc_rate(cnt[j]); cnt[j] = 1; }   // enc:735 (cnt_prev is constant during a pass), 754-758
-        double e_run = 0.0;
+        // enc:743 err += sqrt(d / D), in point order, Double.  The square roots of a tile of 32 points are taken by the
+        // 32 lanes at once after the tile (lane l keeps point l's distance), and the ordered Double additions of that
+        // tile ride along with the next tile's points, one per point: 3 instructions per point in warp 0 instead of a
+        // sqrt + convert + add in every thread, and off the dependency chain of the centroids.
+        double e_run = 0.0, es_prev = 0.0;
+        int tn_prev = 0;
         int par = 0;
+        float xn[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) xn[k] = 0.0f;
+        if (N > 0) gsc_load_row<D>(Xf, 0, xn);                                              // every lane the same row: one broadcast load
         for (int base = 0; base < N; base += 32) {
             const int tn = min(32, N - base);
-            float xt[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) xt[k] = 0.0f;
-            if (lane < tn) gsc_load_row<D>(Xf, base + lane, xt);
             int mylab = 0;
+            float mydw = 0.0f;
+#pragma unroll 2
             for (int p = 0; p < tn; ++p, par ^= 1) {
                 float x[D];
 #pragma unroll
-                for (int k = 0; k < D; ++k) x[k] = __shfl_sync(FULL, xt[k], p);
+                for (int k = 0; k < D; ++k) x[k] = xn[k];
+                gsc_load_row<D>(Xf, min(base + p + 1, N - 1), xn);                  // the next point, a whole step ahead of its use
                 // nearest of this lane's rows: ascending j = ascending centroid index, strict < keeps the lowest
-                float bd = INFINITY;
-                int bj = -1;
+                // (two half-length compare chains merged with a strict <: the same winner as one chain, half the depth)
+                float bd = INFINITY, bdh = INFINITY;
+                int bj = -1, bjh = -1;
+                {
+                    // gsc_ann_dist2 for all row pairs, written dimension by dimension so that the CPL/2 independent
+                    // chains advance together (one pair after the other leaves dependent packed ops back to back)
+                    unsigned long long d2[CPL / 2];
 #pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                    const float d = gsc_ann_dist<D>(x, c[j]);
-                    if (d < bd) { bd = d; bj = j; }
+                    for (int k = 0; k < D; ++k) {
+                        unsigned long long t[CPL / 2], mq[CPL / 2];
+                        const unsigned long long xk = gsc_pk2f(x[k], x[k]);
+#pragma unroll
+                        for (int q = 0; q < CPL / 2; ++q) asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t[q]) : "l"(xk), "l"(c2[q][k]));
+#pragma unroll
+                        for (int q = 0; q < CPL / 2; ++q) asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(mq[q]) : "l"(t[q]), "l"(t[q]));
+#pragma unroll
+                        for (int q = 0; q < CPL / 2; ++q) {
+                            if (k == 0) d2[q] = mq[q];          // 0 + m == m: a square is +0, positive or NaN
+                            else asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d2[q]) : "l"(mq[q]), "l"(ones), "l"(d2[q]));
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < CPL / 2; ++q) {
+                        float da, db;
+                        gsc_upk2f(d2[q], da, db);
+                        if (CPL < 8 || q < CPL / 4) {
+                            if (da < bd) { bd = da; bj = 2 * q; }
+                            if (db < bd) { bd = db; bj = 2 * q + 1; }
+                        } else {
+                            if (da < bdh) { bdh = da; bjh = 2 * q; }
+                            if (db < bdh) { bdh = db; bjh = 2 * q + 1; }
+                        }
+                    }
                 }
+                if (bdh < bd) { bd = bdh; bj = bjh; }
                 const unsigned dk = (bj >= 0) ? __float_as_uint(bd) : 0xffffffffu;      // distances are >= 0: bits order them
                 unsigned m = __reduce_min_sync(FULL, dk);
                 unsigned ci = __reduce_min_sync(FULL, (dk == m && bj >= 0) ? (unsigned)(warp * (32 * CPL) + lane + 32 * bj) : 0xffffffffu);
                 if (WPF == 2) {
-                    if (lane == 0) s_key[par][warp] = ((unsigned long long)m << 32) | ci;
+                    // the two warps' (distance, index) keys meet in shared memory: slot [par][warp], 8 bytes each
+                    if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sk_mine + 16u * par), "r"(ci), "r"(m) : "memory");
                     __syncthreads();
-                    const unsigned long long o = s_key[par][warp ^ 1], mine = ((unsigned long long)m << 32) | ci;
-                    const unsigned long long w2 = o < mine ? o : mine;
-                    m = (unsigned)(w2 >> 32); ci = (unsigned)(w2 & 0xffffffffu);
+                    unsigned oc, om;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(oc), "=r"(om) : "r"(sk_other + 16u * par) : "memory");
+                    const bool take = (om < m) || (om == m && oc < ci);
+                    m = take ? om : m; ci = take ? oc : ci;
                 }
-                int win = (int)ci;
                 float dw = __uint_as_float(m);
-                if (ci == 0xffffffffu) { win = 0; dw = INFINITY; }                       // every row NaN: centroid 0, d = +inf
-                if (warp == win / (32 * CPL) && lane == (win & 31)) {
-                    // enc:735-740, 744 on the winning row (static register indices: one case per owned row)
-                    switch ((win % (32 * CPL)) >> 5) {
-#define GSC_OW_CASE(J) case J: if (J < CPL) { _Pragma("unroll") for (int k = 0; k < D; ++k) { const float v = x[k] - c[J < CPL ? J : 0][k]; const float mm = v * rate[J < CPL ? J : 0]; c[J < CPL ? J : 0][k] = c[J < CPL ? J : 0][k] + mm; } cnt[J < CPL ? J : 0] += 1; } break;
-                        GSC_OW_CASE(0) GSC_OW_CASE(1) GSC_OW_CASE(2) GSC_OW_CASE(3)
-                        GSC_OW_CASE(4) GSC_OW_CASE(5) GSC_OW_CASE(6) GSC_OW_CASE(7)
-#undef GSC_OW_CASE
-                        default: break;
+                if (ci == 0xffffffffu) { ci = 0; dw = INFINITY; }                        // every row NaN: centroid 0, d = +inf
+                const int win = (int)ci;
+                constexpr int LOG_CPL = (CPL == 8) ? 3 : (CPL == 4) ? 2 : (CPL == 2) ? 1 : 0;
+                static_assert((1 << LOG_CPL) == CPL, "rows per lane must be a power of two");
+                if ((unsigned)warp == (ci >> (5 + LOG_CPL)) && (unsigned)lane == (ci & 31u)) {
+                    // enc:735-740, 744 on the winning row (static register indices: a branch tree over the owned rows)
+                    const unsigned wj = (ci >> 5) & (unsigned)(CPL - 1);
+#define GSC_OW_UPD(J) { gsc_ow_update2<D, ((J) < CPL ? (J) : 0) & 1>(c2[((J) < CPL ? (J) : 0) >> 1], x, rate[(J) < CPL ? (J) : 0]); cnt[(J) < CPL ? (J) : 0] += 1; }
+                    if (CPL <= 4 || wj < 4) {
+                        if (CPL <= 2 || (wj & 3u) < 2) { if (CPL <= 1 || (wj & 1u) == 0) GSC_OW_UPD(0) else GSC_OW_UPD(1) }
+                        else { if ((wj & 1u) == 0) GSC_OW_UPD(2) else GSC_OW_UPD(3) }
+                    } else {
+                        if ((wj & 3u) < 2) { if ((wj & 1u) == 0) GSC_OW_UPD(4) else GSC_OW_UPD(5) }
+                        else { if ((wj & 1u) == 0) GSC_OW_UPD(6) else GSC_OW_UPD(7) }
                     }
+#undef GSC_OW_UPD
                 }
-                if (lane == p) mylab = win;                                             // enc:742
-                e_run += (double)sqrtf(dw / (float)D);                                  // enc:743 (same value in every thread)
+                if (lane == p) { mylab = win; mydw = dw; }                              // enc:742
+                const double ev = __shfl_sync(FULL, es_prev, p);
+                if (p < tn_prev) e_run += ev;                                           // only warp 0's sum is used
             }
-            if (warp == 0 && lane < tn) lab[base + lane] = mylab;
+            if (warp == 0) {
+                for (int p = tn; p < tn_prev; ++p) e_run += __shfl_sync(FULL, es_prev, p);   // only when the last tile is short
+                if (lane < tn) lab[base + lane] = mylab;
+                es_prev = (double)sqrtf(mydw / (float)D);
+                tn_prev = tn;
+            }
         }
-        err = e_run;
+        bool same = false;
+        if (warp == 0) {
+            for (int p = 0; p < tn_prev; ++p) e_run += __shfl_sync(FULL, es_prev, p);
+            err = e_run;
+            same = (err > prevErr) ? ((err - prevErr) <= tol) : ((prevErr - err) <= tol);   // enc:761
+        }
         ++iter;
-        const bool same = (err > prevErr) ? ((err - prevErr) <= tol) : ((prevErr - err) <= tol);   // enc:761
+        if (WPF == 2) {
+            if (threadIdx.x == 0) s_stop = same ? 1 : 0;
+            __syncthreads();
+            same = s_stop != 0;
+        }
         if (same || iter >= max_passes) break;
     }
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-        const int ci = warp * (32 * CPL) + lane + 32 * j;
-        if (ci < K) {
+    for (int q = 0; q < CPL / 2; ++q) {
+        const int ca = warp * (32 * CPL) + lane + 32 * (2 * q), cb = ca + 32;
 #pragma unroll
-            for (int k = 0; k < D; ++k) cf[(long long)ci * D + k] = c[j][k];
+        for (int k = 0; k < D; ++k) {
+            float a, b;
+            gsc_upk2f(c2[q][k], a, b);
+            if (ca < K) cf[(long long)ca * D + k] = a;
+            if (cb < K) cf[(long long)cb * D + k] = b;
         }
     }
     if (threadIdx.x == 0) { passes_out[f.slot] = iter; err_out[f.slot] = err; }
-    (void)s_stop;
 }

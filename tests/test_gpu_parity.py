@@ -147,21 +147,23 @@ def test_online_kmeans_bit_exact(ctx, oracle, K, seconds, passes):
 
 
 @pytest.mark.parametrize("K,seconds,passes,D", [(256, 0.25, 100, 8), (100, 0.1, 9, 8), (33, 0.1, 30, 8), (200, 0.15, 12, 4)])
-def test_online_small_dictionary_both_kernels(ctx, oracle, K, seconds, passes, D):
-    """K <= 256 runs one warp per frame with the codebook in registers (k_online_warp); the batched CTA-per-frame
-    kernel stays available (GSC_DBG_ONLINE_BATCHED): both must be the oracle bit for bit."""
+def test_online_small_dictionary_both_kernels(ctx, oracle, K, seconds, passes, D, monkeypatch):
+    """K <= 256 runs one warp per frame with the codebook in registers (k_online_warp; GSC_OW_WARPS=2 splits the
+    codebook over two warps); the batched CTA-per-frame kernel stays available (GSC_DBG_ONLINE_BATCHED): all three
+    must be the oracle bit for bit."""
     pcm, raw, attr, feat = _features(oracle, seconds)
     feat = np.ascontiguousarray(feat[:, :D])
     c0, _, _ = oracle.yakmo(feat, K)
     ref = oracle.knn_scan_reduce(feat, c0, 3, passes)
-    for flag in (0, ctx.DBG_ONLINE_BATCHED):
+    for flag, warps in ((0, "1"), (0, "2"), (ctx.DBG_ONLINE_BATCHED, "1")):
+        monkeypatch.setenv("GSC_OW_WARPS", warps)
         ctx.set_debug(flag)
         try:
             got = ctx.knn_scan_reduce(feat, c0, 3, passes)
         finally:
             ctx.set_debug(0)
-        assert got[2] == ref[2] and got[3] == ref[3], flag
-        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0].view(np.uint32), ref[0].view(np.uint32)), flag
+        assert got[2] == ref[2] and got[3] == ref[3], (flag, warps)
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0].view(np.uint32), ref[0].view(np.uint32)), (flag, warps)
 
 
 def test_online_kmeans_filter_equals_exhaustive(ctx, oracle):
