@@ -136,6 +136,7 @@ struct gsc_ctx {
     // half (few busy SMs) overlaps the seeding of the other
     gsc_ctx *peer = nullptr;
     bool split = false;
+    int batch_total = 0;             // frames of the batch in flight over both lanes (0: single-stage call)
     std::vector<int> idx_a, idx_b;   // frames of the last split batch handled by this context / by the peer
     double stage_t[8] = {};          // start of stage i (ev[i]) in ms after the batch's fork event, filled at fetch
     // .gsc stream of the last batch: packed once (k_pack_frames), sizes kept for the second gsc_fetch_stream call
@@ -332,8 +333,8 @@ static int plan_batch(gsc_ctx *c, const gsc_frame_desc *fr, int F, int cs, int K
 // The single-frame stage calls re-plan the context: whatever a previous gsc_encode_frames batch left behind
 // (lane split, packed stream) no longer describes the buffers.
 static void forget_batch(gsc_ctx *c) {
-    c->split = false; c->idx_a.clear(); c->idx_b.clear(); c->packed = false;
-    if (c->peer) c->peer->packed = false;
+    c->split = false; c->idx_a.clear(); c->idx_b.clear(); c->packed = false; c->batch_total = 0;
+    if (c->peer) { c->peer->packed = false; c->peer->batch_total = 0; }
 }
 
 static int upload_frames(gsc_ctx *c) {
@@ -534,6 +535,8 @@ static int stage_lloyd_update(gsc_ctx *c, int D) {
     return stage_lloyd_means(c, D, c->sums.as<double>());
 }
 
+#define GSC_OW_SPLIT_BELOW (148 * 6)   // frames in flight (both lanes) up to which k_online_warp runs two warps per frame (measured: 148, 592, 888 frames faster with two, 1184 with one)
+
 // Slack on the candidate threshold of the online kernel (a tuning knob: any value gives the same
 // results, see gsc_online.cuh phase 2).  GSC_ONLINE_SLACK overrides the default.
 static float online_slack() {
@@ -605,8 +608,11 @@ static int stage_online(gsc_ctx *c, int D, int precision, int max_passes) {
     // compile without register spills are used (build.py checks).
     // K <= 256: one warp per frame, the codebook in registers, the rule run literally (k_online_warp)
     if (K <= 32 * GSC_OW_CPL && !(c->debug & GSC_DBG_ONLINE_BATCHED) && (D == 8 || D == 4)) {
-        const char *we = getenv("GSC_OW_WARPS");                  // warps per frame: 1 (default), 2 = the codebook split over two warps
-        const int wpf = (we && atoi(we) == 2) ? 2 : 1;
+        // warps per frame: one when the batch fills the SMs with frames (fewest instructions per point), two (the codebook
+        // split over two warps) when it does not: a frame alone on a scheduler is bound by the latency of a point,
+        // which two warps shorten.  GSC_OW_WARPS = 1 | 2 overrides.
+        const char *we = getenv("GSC_OW_WARPS");
+        const int wpf = (we && (atoi(we) == 1 || atoi(we) == 2)) ? atoi(we) : ((c->batch_total > c->F ? c->batch_total : c->F) <= GSC_OW_SPLIT_BELOW ? 2 : 1);
 #define GSC_OW_LAUNCH(DD, WW)                                                                                        \
         LAUNCH(c, (k_online_warp<DD, WW>), c->F, 32 * WW, 0, c->frames.as<GscFrame>(), c->F, c->feat.as<float>(),    \
                c->cen.as<float>(), c->labels.as<int>(), c->passes.as<int>(), c->err.as<double>(), tol, max_passes, c->Kmax, 1.0f)
@@ -1430,6 +1436,8 @@ static int plan_lanes(gsc_ctx *c, int n_frames) {
 template <class Launch>
 static int launch_lanes(gsc_ctx *c, const gsc_frame_desc *frames, int n_frames, const gsc_params *P, Launch launch) {
     TRY(plan_lanes(c, n_frames));
+    c->batch_total = n_frames;
+    if (c->peer) c->peer->batch_total = c->split ? n_frames : 0;
     if (!c->split) return launch(c, frames, n_frames, P);
     std::vector<gsc_frame_desc> fa, fb;
     for (int i : c->idx_a) fa.push_back(frames[i]);
