@@ -426,14 +426,15 @@ static int seed_launch(gsc_ctx *c, int init_type, bool want_seeds) {
     LAUNCH(c, k_seed_prep<D>, c->F, 512, 0, c->frames.as<GscFrame>(), c->feat.as<float>(), c->pnorm.as<float>(),
            c->perm.as<int>(), c->pns.as<float>(), c->xs.as<float>(), c->blo.as<float>(), c->bhi.as<float>());
     // CTA shape: threads x resident CTAs per SM the register allocation is sized for (GSC_SEED_SHAPE = "256x2" ...)
-    static const int seed_shape = [] {
-        const char *e = getenv("GSC_SEED_SHAPE");
-        // measured on 1184 bench frames (wall of the whole batch): 256x2 11.01 s, 256x3 10.86 s, 128x4 10.61 s, 128x6 10.77 s
-        if (e && !strcmp(e, "256x2")) return 0;
-        if (e && !strcmp(e, "256x3")) return 1;
-        if (e && !strcmp(e, "128x6")) return 3;
-        return 2;
-    }();
+    // measured on 1184 bench frames (wall of the whole batch): 256x2 11.01 s, 256x3 10.86 s, 128x4 10.61 s, 128x6 10.77 s;
+    // with at most two frames per SM in flight the 256-thread CTAs are faster (148 frames per launch: 231 vs 320 ms)
+    int seed_shape = ((c->batch_total > c->F ? c->batch_total : c->F) <= 2 * 148) ? 0 : 2;
+    if (const char *e = getenv("GSC_SEED_SHAPE")) {       // override, read per call (tests run every shape)
+        if (!strcmp(e, "256x2")) seed_shape = 0;
+        else if (!strcmp(e, "256x3")) seed_shape = 1;
+        else if (!strcmp(e, "128x4")) seed_shape = 2;
+        else if (!strcmp(e, "128x6")) seed_shape = 3;
+    }
 #define GSC_SEED2_LAUNCH(TT, MB)                                                                                          \
     do {                                                                                                                  \
         SMEM_OPTIN((k_seed2<D, TT, MB>), smem);                                                                           \

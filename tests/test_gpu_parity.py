@@ -125,6 +125,18 @@ def test_yakmo_seeding_edge_cases(ctx, oracle, kind):
     assert _same_f32(c_gpu, c_ref) and np.array_equal(l_gpu, l_ref)
 
 
+@pytest.mark.parametrize("shape", ["256x2", "256x3", "128x4", "128x6"])
+def test_yakmo_seeding_cta_shapes(ctx, oracle, shape, monkeypatch):
+    """k_seed2 is instantiated for four CTA shapes (threads x resident CTAs per SM; the library picks by batch size,
+    GSC_SEED_SHAPE overrides): each must give the oracle's seed sequence."""
+    pcm, raw, attr, feat = _features(oracle, 0.6)
+    c_ref, l_ref, s_ref = oracle.yakmo(feat, 700)
+    monkeypatch.setenv("GSC_SEED_SHAPE", shape)
+    c_gpu, l_gpu, s_gpu = ctx.yakmo(feat, 700)
+    assert np.array_equal(s_gpu, s_ref), f"{shape}: first divergence at seed {int(np.argmax(s_gpu != s_ref))}"
+    assert _same_f32(c_gpu, c_ref) and np.array_equal(l_gpu, l_ref)
+
+
 def test_yakmo_random_init_and_iters(ctx, oracle):
     pcm, raw, attr, feat = _features(oracle, 0.1)
     c_ref, l_ref, s_ref = oracle.yakmo(feat, 32, init_type=0, max_iter=0)
