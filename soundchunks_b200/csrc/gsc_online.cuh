@@ -899,39 +899,19 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
 // With 256 centroids the whole codebook fits the warp's registers (lane l owns centroids l, l+32, ... l+224: 8 rows
 // of D floats), so the reference's rule (enc:699-765) is run literally, one point after the other, with no
 // batching, speculation or block barrier: every lane scores the point against its 8 rows in the exact operation
-// order (ANN: sum (x-c)^2 left to right, no FMA), two redux steps give the nearest centroid with the lowest index on
+// order (ANN: sum (x-c)^2 left to right, two roundings per term; rows held in PAIRS as packed registers so that one
+// FADD2 / FMUL2 / FFMA2-by-one serves two rows, gsc_ann_dist2), two redux steps give the nearest centroid with the lowest index on
 // ties, the owning lane moves its row.  The per-batch machinery of k_online (filter, lists, resolver rounds, three
 // block barriers per batch) costs more than scoring 256 centroids outright; here the warps of an SM are independent
 // frames and keep its issue slots busy.  Every lane reads the point itself (one broadcast load, issued a whole point
 // ahead of its use); labels are written back coalesced per tile of 32 points; the Double error sum is taken in point
 // order by warp 0, one tile behind (see the pass loop).
-// grid = ceil(F / GSC_OW_WARPS), block = 32 * GSC_OW_WARPS.
+// grid = F, block = 32 * WPF.
 // ---------------------------------------------------------------------------
 #define GSC_OW_CPL 8          // centroids per lane with one warp per frame (K <= 256)
 
-// enc:735-740, 744 on one codebook row: v = x - c; m = v * rate; c = c + m.  Subtractions and products in pairs through the
-// packed FP32 pipe (bit for bit the scalar results), the final additions scalar (see gsc_ann_dist on why not packed).
-template <int D>
-__device__ __forceinline__ void gsc_ow_update(float (&c)[D], const float (&x)[D], float rate) {
-    if (D % 2 == 0) {
-        const unsigned long long r2 = gsc_pk2f(rate, rate);
-#pragma unroll
-        for (int k = 0; k < D / 2; ++k) {
-            unsigned long long t, m;
-            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(gsc_pk2f(x[2 * k], x[2 * k + 1])), "l"(gsc_pk2f(c[2 * k], c[2 * k + 1])));
-            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(m) : "l"(t), "l"(r2));
-            float m0, m1;
-            gsc_upk2f(m, m0, m1);
-            c[2 * k] = c[2 * k] + m0;
-            c[2 * k + 1] = c[2 * k + 1] + m1;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < D; ++k) { const float v = x[k] - c[k]; const float mm = v * rate; c[k] = c[k] + mm; }
-    }
-}
-
-// the same on row H (0 or 1) of a packed pair of rows
+// enc:735-740, 744 on one codebook row: v = x - c; m = v * rate; c = c + m (scalar: the row is one half of a packed
+// pair of rows), H = 0 or 1 selects the half
 template <int D, int H>
 __device__ __forceinline__ void gsc_ow_update2(unsigned long long (&c2)[D], const float (&x)[D], float rate) {
 #pragma unroll
