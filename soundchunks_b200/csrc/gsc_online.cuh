@@ -402,10 +402,27 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                     c0lo = fminf(c0lo, rows[j][0]); c0hi = fmaxf(c0hi, rows[j][0]);
                 }
                 gsc_sts_i(sb + Ly::DIRTY + 4u * cell, 0);
-                for (int j = tid; j < N; j += T) lab[j] = gsc_lds_u16(sb + Ly::FK + 2u * (unsigned)lab[j]);   // labels are slots
+                for (int j = tid; j < N; j += 4 * T) {   // labels are slots (4 independent loads in flight per thread)
+                    int v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = (j + q * T < N) ? lab[j + q * T] : 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (j + q * T < N) lab[j + q * T] = gsc_lds_u16(sb + Ly::FK + 2u * (unsigned)v[q]);
+                }
                 __syncthreads();
             }
-            for (int t = tid; t < tn * D; t += T) gsc_sts_f(sb + Ly::X + 4u * t, Xf[(long long)base * D + t]);
+            {   // the tile's rows, 16 bytes per access, two loads in flight per thread (D is a multiple of 4: rows are 16-byte aligned)
+                static_assert(D % 4 == 0, "rows copied in 16-byte pieces");
+                const float4 *src = reinterpret_cast<const float4 *>(Xf + (long long)base * D);
+                const int nv = tn * (D / 4);
+                for (int t = tid; t < nv; t += 2 * T) {
+                    const bool two = t + T < nv;
+                    const float4 v0 = src[t];
+                    const float4 v1 = two ? src[t + T] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gsc_sts_f4(sb + Ly::X + 16u * (unsigned)t, v0);
+                    if (two) gsc_sts_f4(sb + Ly::X + 16u * (unsigned)(t + T), v1);
+                }
+            }
             for (int t = tid; t < tn; t += T) {
                 int gg = lab[base + t];
                 GSC_CHK(gg >= 0 && gg < KP);
@@ -419,6 +436,16 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
                 gsc_sts_f(sb + Ly::HX + 4u * t, 0.5f * nx * (1.0f - GSC_ON_G) - 1e-30f);
             }
             __syncthreads();  // (C)
+            {   // the next tile's rows and labels (tile 0 of the next pass after the last one) start their way up the cache
+                // hierarchy now: their load at the tile switch is synchronous and otherwise pays the DRAM latency
+                // (measured: k-means stage -1 %; issuing it one batch before the switch instead costs a register)
+                const int nbase = (base + GSC_ON_TP < N) ? base + GSC_ON_TP : 0;
+                const int nn = min(GSC_ON_TP, N - nbase);
+                const char *px = reinterpret_cast<const char *>(Xf + (long long)nbase * D);
+                const char *pl = reinterpret_cast<const char *>(lab + nbase);
+                for (int t = tid; t < (nn * D * 4 + 127) / 128; t += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(px + 128 * t));
+                for (int t = tid; t < (nn * 4 + 127) / 128; t += T) asm volatile("prefetch.global.L1 [%0];" ::"l"(pl + 128 * t));
+            }
 
             for (int pos = 0; pos < tn; pos += B) {
                 const int nb = min(B, tn - pos);
