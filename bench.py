@@ -12,8 +12,10 @@ the data path; torch.distributed is only the barrier and the max-over-ranks of t
 
 Prints ONE JSON line (rank 0).  `value` = audio-seconds per second with the PCM already resident
 in HBM (gsc_encode_frames_dev, CUDA events on the library's stream); `e2e` = the same metric
-through the public host-buffer call gsc_encode_frames (pinned staging + H2D + all kernels + D2H of
-dictionary/indexes inside the timed region).
+through the public host-buffer call gsc_encode_frames + gsc_fetch_stream (pinned staging + H2D + all
+kernels + the device-side packer + ONE D2H of the .gsc stream's bytes inside the timed region).
+Further keys: roofline (k_online, FP32), cpu_baseline, parity_check, lloyd_mode, and the
+BASELINE.json configs[2..4] legs k256, strong_1h, split_frame (--no-extras skips them).
 
 --impl reference times the CPU restatement of the reference (oracle/, all host threads) on a
 bounded sample of the SAME workload: one 4 s frame of the same generator per host core and step,

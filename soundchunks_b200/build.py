@@ -67,8 +67,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 def online_spills(ptxas_log: str) -> list:
     """Names of k_online instantiations that ptxas compiled with spill stores.
 
-    The online k-means kernel sits at the 255-register limit; builds of its largest shape that spilled have
-    produced results that differ from the spill-free build, so a spilling shape is treated as a build error."""
+    The online k-means kernel sits at the 255-register limit.  Round 1 reported that a spilling build of its largest
+    shape gave different results; round 2 could not reproduce that (147 of 147 forced-spill runs bit-identical,
+    profiles/r2_spill_probe.md), so spills are a PERFORMANCE matter: local-memory traffic in
+    the innermost loops of a latency-bound kernel.  A spilling shape is still treated as a build error so that a
+    compiler update cannot slow the dispatched shapes down unnoticed."""
     bad, cur = [], None
     for line in ptxas_log.splitlines():
         if "Compiling entry function" in line:
