@@ -438,7 +438,7 @@ __global__ void GSC_ONLINE_BOUNDS(T) k_online(const GscFrame *__restrict__ frame
             __syncthreads();  // (C)
             {   // the next tile's rows and labels (tile 0 of the next pass after the last one) start their way up the cache
                 // hierarchy now: their load at the tile switch is synchronous and otherwise pays the DRAM latency
-                // (measured: k-means stage -1 %; issuing it one batch before the switch instead costs a register)
+                // (measured: k-means stage -1 %; issuing it one batch before the switch instead costs a register and was no faster)
                 const int nbase = (base + GSC_ON_TP < N) ? base + GSC_ON_TP : 0;
                 const int nn = min(GSC_ON_TP, N - nbase);
                 const char *px = reinterpret_cast<const char *>(Xf + (long long)nbase * D);
